@@ -1,0 +1,235 @@
+/*
+ * rgbd_b200 — C-ABI of the B200-native ELIC_united compress/decompress hot path.
+ *
+ * Plain pointers and sizes only (no torch / pybind types).  Every device pointer is a raw
+ * CUDA device address, every `stream` a cudaStream_t passed as void*.  All functions return
+ * 0 on success or a negative RGBD_E_* code and never throw; nothing allocates device
+ * memory behind the caller's back (work buffers are passed in).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * reference repository root):
+ *
+ *   CompressAI/compressai/cpp_exts/rans/rans_interface.cpp   (module compressai.ans)
+ *   CompressAI/compressai/cpp_exts/ops/ops.cpp               (module compressai._CXX)
+ *   CompressAI/compressai/entropy_models/entropy_models.py   (quantize / build_indexes / likelihood)
+ *   utils/ckbd.py                                            (checkerboard squeeze / unsqueeze)
+ *   modules/transform/*.py, modules/layers/*.py              (conv / deconv / SE / ESA blocks)
+ *
+ * Activation layout in HBM: NHWC ("pixels"), a tensor view is (base pointer, channel
+ * stride of one pixel in elements = `cstride`, first channel = `coff`, channel count).
+ * Concatenations of the reference (torch.cat on dim 1) are therefore views of one wider
+ * buffer that several producers write at different `coff`.
+ */
+#ifndef RGBD_B200_H
+#define RGBD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGBD_OK 0
+#define RGBD_E_INVALID (-1)   /* bad argument */
+#define RGBD_E_CUDA (-2)      /* CUDA runtime error, see rgbd_last_error() */
+#define RGBD_E_CAPACITY (-3)  /* output buffer too small */
+#define RGBD_E_UNSUPPORTED (-4)
+
+#define RGBD_DT_F32 0
+#define RGBD_DT_BF16 1
+
+#define RGBD_ACT_NONE 0
+#define RGBD_ACT_RELU 1
+#define RGBD_ACT_LEAKY 2 /* negative slope 0.01 (nn.LeakyReLU default) */
+
+/* epilogue modes of the conv kernels; v = acc + bias */
+#define RGBD_EPI_LINEAR 0   /* y = act(v + res)                  res optional            */
+#define RGBD_EPI_GATE 1     /* y = res + mul * sigmoid(v)        res optional, mul required */
+#define RGBD_EPI_BILERP 2   /* y = act(v + bilinear_upsample(res)) res = small NHWC map     */
+
+#define RGBD_MAX_TAPS 25
+
+const char *rgbd_last_error(void);
+int rgbd_abi_version(void);
+/* number of kernels this library has launched since the last reset (bench bookkeeping) */
+int64_t rgbd_launch_count(int reset);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution family (implicit GEMM over NHWC pixels).
+ * Replaces nn.Conv2d / nn.ConvTranspose2d as used by modules/layers/conv.py:7-34,
+ * modules/layers/res_blk.py:7-27, modules/transform/{analysis,synthesis,attention,context,
+ * entropy}.py and compressai/layers/layers.py:162-213.
+ *
+ * One launch computes, for every image n and every output site (oy, ox) of an Hs x Ws
+ * sub-lattice,
+ *     acc[co] = sum_t sum_ci  x[n, oy*i_step + dy[t], ox*i_step + dx[t], ci] * in_scale[n,ci]
+ *                              * w[wtap[t]][ci][co]
+ * (out-of-range input sites contribute zero = the reference's zero padding) and stores the
+ * epilogue result at output pixel (oy*o_step + o_off_y, ox*o_step + o_off_x).
+ * A strided Conv2d is i_step = stride, dy = ky - pad; a ConvTranspose2d(k5,s2,p2,op1) is four
+ * launches (one per output parity) with o_step = 2; ConvTranspose2d(k3,s1,p1) is dy = 1 - ky.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct rgbd_conv_desc {
+    const void *x;          /* input pixels */
+    void *y;                /* output pixels */
+    void *y2;               /* optional second copy of the output (same dtype), may be NULL */
+    const void *w;          /* packed weights, see rgbd_conv_weight_elems() */
+    const float *bias;      /* [Cout] or NULL */
+    const void *res;        /* optional, dtype = x_dtype */
+    const void *mul;        /* optional, dtype = x_dtype */
+    const float *in_scale;  /* optional [N][Cin] per-image input-channel scale (SE folding) */
+    int32_t N, H, W;        /* input dims */
+    int32_t Cin, x_cstride, x_coff;
+    int32_t Ho, Wo;         /* full output dims */
+    int32_t Cout, y_cstride, y_coff;
+    int32_t y2_cstride, y2_coff;
+    int32_t Hs, Ws, o_step, o_off_y, o_off_x, i_step;
+    int32_t ntaps;
+    int32_t res_cstride, res_coff, res_H, res_W; /* res_H/W only for RGBD_EPI_BILERP */
+    int32_t mul_cstride, mul_coff;
+    int32_t act, epi;
+    int32_t x_dtype, y_dtype; /* RGBD_DT_* */
+    int32_t cout_pad;         /* packed weight row length (multiple of 16) */
+    int8_t dy[RGBD_MAX_TAPS], dx[RGBD_MAX_TAPS];
+    int8_t wtap[RGBD_MAX_TAPS];
+    int8_t _pad[5];
+} rgbd_conv_desc;
+
+/* fp32-accumulate CUDA-core path: weights fp32 [ntaps_total][Cin][cout_pad]. Used for the
+ * fp32 parity mode and for the 3/1-channel image-side layers. */
+int rgbd_conv_simt(const rgbd_conv_desc *d, void *stream);
+
+/* tcgen05 tensor-core path (bf16 operands, fp32 TMEM accumulators, TMA-staged NHWC tiles).
+ * Weights bf16 [ntaps_total][cout_pad][cin_pad] (K-major).  The plan object owns the TMA
+ * descriptors for (x, w) so that a launch is a single kernel. */
+typedef struct rgbd_conv_tc_plan rgbd_conv_tc_plan;
+int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad, rgbd_conv_tc_plan **out);
+int rgbd_conv_tc_run(const rgbd_conv_tc_plan *p, void *stream);
+void rgbd_conv_tc_plan_destroy(rgbd_conv_tc_plan *p);
+
+/* ------------------------------------------------------------------------------------------
+ * Small spatial / channel ops of the transforms.
+ * ------------------------------------------------------------------------------------------ */
+/* SE_Block (modules/transform/attention.py:52-67): s[n,c] = sigmoid(W2 relu(W1 mean_hw x)).
+ * `partial` is a work buffer of N*nchunk*C floats; out scale[n,c] = s (+1 if plus_one, which
+ * folds EntropyParametersEX's `x + se(x)`, modules/transform/entropy.py:75). Deterministic
+ * fixed-order reduction, independent of N. */
+int rgbd_se_scale(const void *x, int32_t dtype, int32_t N, int32_t HW, int32_t C, int32_t cstride,
+                  int32_t coff, const float *w1, const float *w2, int32_t Cr, int32_t plus_one,
+                  float *partial, int32_t nchunk, float *scale, void *stream);
+/* F.max_pool2d(kernel 7, stride 3) of ESA (attention.py:88) */
+int rgbd_maxpool7s3(const void *x, void *y, int32_t dtype, int32_t N, int32_t H, int32_t W,
+                    int32_t C, void *stream);
+/* NCHW fp32 image -> NHWC (dtype), and back with optional clamp to [0,1] (elic_united.py:452) */
+int rgbd_nchw_to_nhwc(const float *x, void *y, int32_t dtype, int32_t N, int32_t C, int32_t H,
+                      int32_t W, int32_t y_cstride, int32_t y_coff, void *stream);
+int rgbd_nhwc_to_nchw(const void *x, int32_t dtype, float *y, int32_t N, int32_t C, int32_t H,
+                      int32_t W, int32_t x_cstride, int32_t x_coff, int32_t clamp01, void *stream);
+
+/* torch.cat plumbing: copy the channel slice of one NHWC view into another (same dtype), and an
+ * async memset for the zero-initialised y_hat buffers (utils/ckbd.py:37-48 `torch.zeros_like`). */
+int rgbd_copy_view(const void *x, void *y, int32_t dtype, int64_t npix, int32_t C, int32_t x_cstride,
+                   int32_t x_coff, int32_t y_cstride, int32_t y_coff, void *stream);
+int rgbd_zero(void *p, int64_t bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Gaussian-conditional entropy model, checkerboard-fused.
+ * ------------------------------------------------------------------------------------------ */
+/* One anchor / non-anchor coding step of the encoder: utils/ckbd.py:83-105 fused with
+ * GaussianConditional.build_indexes (entropy_models.py:561-568) and
+ * EntropyModel.quantize("symbols") (entropy_models.py:118-146).
+ *   y      : fp32 NHWC latent, slice = channels [y_coff, y_coff+g)
+ *   params : fp32 NHWC [N,H,W,2g] = (scales | means) (elic_united.py:289)
+ *   parity : 0 = anchor ((h+w) odd), 1 = non-anchor ((h+w) even)
+ * For each image n the g*H*(W/2) selected sites, in (c, h, w/2) row-major order, get
+ *   sym[n*stream_stride + chunk_off + j] = int32(rint(y - mean)),  idx[...] = scale index,
+ * and yhat (dtype) at that site = float(sym) + mean. */
+int rgbd_ckbd_quantize_index(const float *y, int32_t y_cstride, int32_t y_coff,
+                             const float *params, const float *scale_table, int32_t n_scales,
+                             float scale_bound, int32_t N, int32_t H, int32_t W, int32_t g,
+                             int32_t parity, int32_t *sym, uint8_t *idx, int64_t stream_stride,
+                             int64_t chunk_off, void *yhat, int32_t yhat_dtype,
+                             int32_t yhat_cstride, int32_t yhat_coff, void *stream);
+/* Decoder pre-pass: indexes only (utils/ckbd.py:108-112). */
+int rgbd_ckbd_index(const float *params, const float *scale_table, int32_t n_scales,
+                    float scale_bound, int32_t N, int32_t H, int32_t W, int32_t g, int32_t parity,
+                    uint8_t *idx, int64_t stream_stride, int64_t chunk_off, void *stream);
+/* Decoder post-pass: yhat = float(sym) + mean scattered back (utils/ckbd.py:113-114). */
+int rgbd_ckbd_dequant_scatter(const int32_t *sym, int64_t stream_stride, int64_t chunk_off,
+                              const float *params, int32_t N, int32_t H, int32_t W, int32_t g,
+                              int32_t parity, void *yhat, int32_t yhat_dtype,
+                              int32_t yhat_cstride, int32_t yhat_coff, void *stream);
+/* forward(): one coding step of codeOnePart (elic_united.py:94-115) without the coder:
+ * yhat at the parity sites = ste_round(y - mean) + mean, and the likelihood of
+ * GaussianConditional.forward (entropy_models.py:534-558) of the *dequantised* value
+ * written in NCHW fp32 at lik[n, lik_coff + c, h, w]. */
+int rgbd_ckbd_ste_likelihood(const float *y, int32_t y_cstride, int32_t y_coff,
+                             const float *params, float scale_bound, float lik_bound, int32_t N,
+                             int32_t H, int32_t W, int32_t g, int32_t parity, void *yhat,
+                             int32_t yhat_dtype, int32_t yhat_cstride, int32_t yhat_coff,
+                             float *lik, int32_t lik_C, int32_t lik_coff, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Factorised-prior entropy bottleneck (z).
+ * ------------------------------------------------------------------------------------------ */
+/* EntropyBottleneck.compress symbols (entropy_models.py:437-440): sym[n][c*HW + p] =
+ * int32(rint(z - median[c])), idx = c; also zhat = sym + median in NHWC (dtype). */
+int rgbd_eb_quantize(const float *z, int32_t z_cstride, int32_t N, int32_t HW, int32_t C,
+                     const float *medians, int32_t *sym, uint8_t *idx, void *zhat,
+                     int32_t zhat_dtype, int32_t zhat_cstride, int32_t zhat_coff, void *stream);
+/* EntropyBottleneck.decompress dequantise (entropy_models.py:442-446, 262-263) */
+int rgbd_eb_dequantize(const int32_t *sym, int32_t N, int32_t HW, int32_t C, const float *medians,
+                       void *zhat, int32_t zhat_dtype, int32_t zhat_cstride, int32_t zhat_coff,
+                       void *stream);
+/* EntropyBottleneck.forward likelihood (entropy_models.py:369-428) at zhat = ste-rounded z,
+ * likelihood written NCHW fp32; eb_params = packed per-channel parameters [C][59] (see entropy_models.py). */
+int rgbd_eb_likelihood(const float *z, int32_t z_cstride, int32_t N, int32_t HW, int32_t C,
+                       const float *eb_params, float lik_bound, void *zhat, int32_t zhat_dtype,
+                       int32_t zhat_cstride, int32_t zhat_coff, float *lik, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * rANS coder — byte-identical replacement for compressai.ans.
+ * Tables: the int32[n_tables][stride] CDF matrix of the reference is compacted on the host
+ * into one uint16 array (values mod 2^16, like the reference's uint16 casts in
+ * rans_interface.cpp:131-133) plus per-table (base, length, offset).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct rgbd_rans_tables {
+    const uint16_t *cdf;    /* device, sum(length) entries */
+    const int32_t *base;    /* device [n_tables] first entry of table i */
+    const int32_t *length;  /* device [n_tables] = _cdf_length */
+    const int32_t *offset;  /* device [n_tables] = _offset */
+    int32_t n_tables;
+    int32_t total;          /* sum(length) */
+} rgbd_rans_tables;
+
+/* BufferedRansEncoder.encode_with_indexes + flush (rans_interface.cpp:99-192), and
+ * RansEncoder.encode_with_indexes (:194-205), batched: stream s encodes symbols
+ * sym[s*stream_stride .. +n_sym) with the same tables.  Each stream owns cap_words 32-bit
+ * words of `out`; the finished stream is the TAIL of its region: bytes
+ * out + 4*(s*cap_words + cap_words - nwords[s]) .. end.  nwords[s] < 0 flags overflow. */
+int rgbd_rans_encode(const int32_t *sym, const uint8_t *idx, int64_t stream_stride, int32_t n_sym,
+                     int32_t n_streams, const rgbd_rans_tables *t, uint32_t *out,
+                     int64_t cap_words, int32_t *nwords, void *stream);
+
+/* RansDecoder.set_stream (rans_interface.cpp:278-284): state[s] = {x, next word}. */
+typedef struct rgbd_rans_dec_state {
+    uint64_t x;
+    int64_t pos;
+} rgbd_rans_dec_state;
+int rgbd_rans_decode_init(const uint32_t *words, const int64_t *word_off, int32_t n_streams,
+                          rgbd_rans_dec_state *state, void *stream);
+/* RansDecoder.decode_stream / decode_with_indexes (rans_interface.cpp:207-276, 286-351):
+ * continue every stream by n_sym symbols: indexes idx[s*stream_stride + chunk_off ..),
+ * symbols to sym[same].  State persists in device memory between calls. */
+int rgbd_rans_decode_chunk(const uint32_t *words, const int64_t *word_off, const int64_t *word_len,
+                           int32_t n_streams, rgbd_rans_dec_state *state, const uint8_t *idx,
+                           int32_t *sym, int64_t stream_stride, int64_t chunk_off, int32_t n_sym,
+                           const rgbd_rans_tables *t, void *stream);
+
+/* pmf_to_quantized_cdf (ops.cpp:24-81). Host function. cdf has n+1 entries. */
+int rgbd_pmf_to_quantized_cdf(const float *pmf, int32_t n, int32_t precision, uint32_t *cdf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGBD_B200_H */

@@ -1,0 +1,12 @@
+"""B200-native ELIC_united compress/decompress path.
+
+The directory name follows the project naming rule and is not a valid Python identifier;
+import it through the `rgbd_b200` alias module at the repository root
+(`import rgbd_b200`), or `importlib.import_module("learning-based-rgb-d-image-compression_b200")`.
+"""
+from .elic_united import ELIC_united  # noqa: F401
+from .elic_united_r2d import ELIC_united_R2D  # noqa: F401
+from .config import Config, model_config  # noqa: F401
+
+# lookup is by substring in dict order, so the R2D key must come first (models/__init__.py:11-20)
+modelZoo = {"ELIC_united_R2D": ELIC_united_R2D, "ELIC_united": ELIC_united}

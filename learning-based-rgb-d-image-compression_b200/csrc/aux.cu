@@ -1,0 +1,210 @@
+// Small spatial / channel kernels of the transforms: SE_Block channel attention
+// (reference modules/transform/attention.py:52-67), ESA's max-pool (attention.py:88) and the
+// NCHW <-> NHWC boundary conversions (+ the final clamp of elic_united.py:452).
+#include "common.cuh"
+#include <float.h>
+
+namespace {
+
+// partial[n][chunk][c] = sum over the chunk's pixels, fixed order
+template <typename T>
+__global__ void se_partial_kernel(const T *__restrict__ x, int HW, int C, int cstride, int coff,
+                                  int nchunk, float *__restrict__ partial) {
+    const int n = blockIdx.x / nchunk, chunk = blockIdx.x % nchunk;
+    const int per = (HW + nchunk - 1) / nchunk;
+    const int p0 = chunk * per;
+    const int p1 = min(HW, p0 + per);
+    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < C; c += gridDim.y * blockDim.x) {
+        const T *px = x + ((int64_t)n * HW + p0) * cstride + coff + c;
+        float s = 0.f;
+        for (int p = p0; p < p1; ++p, px += cstride) s += ElemIO<T>::ld(px);
+        partial[((int64_t)n * nchunk + chunk) * C + c] = s;
+    }
+}
+
+// one CTA per image: mean -> FC1 + ReLU -> FC2 + sigmoid (+1)
+__global__ void se_fc_kernel(const float *__restrict__ partial, int nchunk, int HW, int C,
+                             const float *__restrict__ w1, const float *__restrict__ w2, int Cr,
+                             int plus_one, float *__restrict__ scale) {
+    extern __shared__ float sm[];
+    float *mean = sm;        // [C]
+    float *hid = sm + C;     // [Cr]
+    const int n = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < nchunk; ++k) s += partial[((int64_t)n * nchunk + k) * C + c];
+        mean[c] = s / (float)HW;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int r = warp; r < Cr; r += nwarp) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(w1[(int64_t)r * C + c], mean[c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) hid[r] = s > 0.f ? s : 0.f;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < Cr; ++r) s = fmaf(w2[(int64_t)c * Cr + r], hid[r], s);
+        const float g = 1.0f / (1.0f + expf(-s));
+        scale[(int64_t)n * C + c] = plus_one ? 1.0f + g : g;
+    }
+}
+
+template <typename T>
+__global__ void maxpool7s3_kernel(const T *__restrict__ x, T *__restrict__ y, int N, int H, int W, int C,
+                                  int Ho, int Wo) {
+    const int64_t total = (int64_t)N * Ho * Wo * C;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C);
+        int64_t r = e / C;
+        const int ox = (int)(r % Wo);
+        r /= Wo;
+        const int oy = (int)(r % Ho);
+        const int n = (int)(r / Ho);
+        float m = -FLT_MAX;
+        for (int ky = 0; ky < 7; ++ky)
+            for (int kx = 0; kx < 7; ++kx) {
+                const float v = ElemIO<T>::ld(x + (((int64_t)n * H + oy * 3 + ky) * W + ox * 3 + kx) * C + c);
+                m = v > m ? v : m;
+            }
+        ElemIO<T>::st(y + e, m);
+    }
+}
+
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float *__restrict__ x, T *__restrict__ y, int N, int C, int H, int W,
+                                    int cstride, int coff) {
+    const int64_t total = (int64_t)N * C * H * W;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t hw = e % ((int64_t)H * W);
+        const int c = (int)((e / ((int64_t)H * W)) % C);
+        const int n = (int)(e / ((int64_t)H * W * C));
+        ElemIO<T>::st(y + ((int64_t)n * H * W + hw) * cstride + coff + c, x[e]);
+    }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T *__restrict__ x, float *__restrict__ y, int N, int C, int H, int W,
+                                    int cstride, int coff, int clamp01) {
+    const int64_t total = (int64_t)N * C * H * W;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t hw = e % ((int64_t)H * W);
+        const int c = (int)((e / ((int64_t)H * W)) % C);
+        const int n = (int)(e / ((int64_t)H * W * C));
+        float v = ElemIO<T>::ld(x + ((int64_t)n * H * W + hw) * cstride + coff + c);
+        if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+        y[e] = v;
+    }
+}
+
+template <typename T>
+__global__ void copy_view_kernel(const T *__restrict__ x, T *__restrict__ y, int64_t npix, int C, int xs, int xo,
+                                 int ys, int yo) {
+    const int64_t total = npix * C;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = e / C;
+        const int c = (int)(e % C);
+        y[p * ys + yo + c] = x[p * xs + xo + c];
+    }
+}
+
+}  // namespace
+
+extern "C" int rgbd_copy_view(const void *x, void *y, int32_t dtype, int64_t npix, int32_t C, int32_t x_cstride,
+                              int32_t x_coff, int32_t y_cstride, int32_t y_coff, void *stream) {
+    RGBD_CHECK_ARG(x && y, "null pointer");
+    RGBD_CHECK_ARG(npix > 0 && C > 0, "dims");
+    const int grid = rgbd_grid_for(npix * C, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == RGBD_DT_F32)
+        copy_view_kernel<float><<<grid, 256, 0, st>>>((const float *)x, (float *)y, npix, C, x_cstride, x_coff,
+                                                      y_cstride, y_coff);
+    else
+        copy_view_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, npix, C,
+                                                               x_cstride, x_coff, y_cstride, y_coff);
+    RGBD_LAUNCH_CHECK();
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_zero(void *p, int64_t bytes, void *stream) {
+    RGBD_CHECK_ARG(p && bytes >= 0, "pointer/size");
+    cudaError_t e = cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        rgbd_set_error("rgbd_zero: %s", cudaGetErrorString(e));
+        return RGBD_E_CUDA;
+    }
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_se_scale(const void *x, int32_t dtype, int32_t N, int32_t HW, int32_t C, int32_t cstride,
+                             int32_t coff, const float *w1, const float *w2, int32_t Cr, int32_t plus_one,
+                             float *partial, int32_t nchunk, float *scale, void *stream) {
+    RGBD_CHECK_ARG(x && w1 && w2 && partial && scale, "null pointer");
+    RGBD_CHECK_ARG(N > 0 && HW > 0 && C > 0 && Cr > 0 && nchunk > 0, "dims");
+    RGBD_CHECK_ARG((size_t)(C + Cr) * 4 <= 48 * 1024, "C too large for the FC kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)(N * nchunk), (unsigned)((C + 127) / 128));
+    if (dtype == RGBD_DT_F32)
+        se_partial_kernel<float><<<grid, 128, 0, st>>>((const float *)x, HW, C, cstride, coff, nchunk, partial);
+    else
+        se_partial_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16 *)x, HW, C, cstride, coff,
+                                                                nchunk, partial);
+    RGBD_LAUNCH_CHECK();
+    se_fc_kernel<<<N, 256, (size_t)(C + Cr) * 4, st>>>(partial, nchunk, HW, C, w1, w2, Cr, plus_one, scale);
+    RGBD_LAUNCH_CHECK();
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_maxpool7s3(const void *x, void *y, int32_t dtype, int32_t N, int32_t H, int32_t W, int32_t C,
+                               void *stream) {
+    RGBD_CHECK_ARG(x && y, "null pointer");
+    RGBD_CHECK_ARG(N > 0 && H >= 7 && W >= 7 && C > 0, "dims (needs H, W >= 7)");
+    const int Ho = (H - 7) / 3 + 1, Wo = (W - 7) / 3 + 1;
+    const int grid = rgbd_grid_for((int64_t)N * Ho * Wo * C, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == RGBD_DT_F32)
+        maxpool7s3_kernel<float><<<grid, 256, 0, st>>>((const float *)x, (float *)y, N, H, W, C, Ho, Wo);
+    else
+        maxpool7s3_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, N, H,
+                                                                W, C, Ho, Wo);
+    RGBD_LAUNCH_CHECK();
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_nchw_to_nhwc(const float *x, void *y, int32_t dtype, int32_t N, int32_t C, int32_t H,
+                                 int32_t W, int32_t y_cstride, int32_t y_coff, void *stream) {
+    RGBD_CHECK_ARG(x && y, "null pointer");
+    RGBD_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0, "dims");
+    const int grid = rgbd_grid_for((int64_t)N * C * H * W, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == RGBD_DT_F32)
+        nchw_to_nhwc_kernel<float><<<grid, 256, 0, st>>>(x, (float *)y, N, C, H, W, y_cstride, y_coff);
+    else
+        nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, (__nv_bfloat16 *)y, N, C, H, W, y_cstride,
+                                                                  y_coff);
+    RGBD_LAUNCH_CHECK();
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_nhwc_to_nchw(const void *x, int32_t dtype, float *y, int32_t N, int32_t C, int32_t H,
+                                 int32_t W, int32_t x_cstride, int32_t x_coff, int32_t clamp01, void *stream) {
+    RGBD_CHECK_ARG(x && y, "null pointer");
+    RGBD_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0, "dims");
+    const int grid = rgbd_grid_for((int64_t)N * C * H * W, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == RGBD_DT_F32)
+        nhwc_to_nchw_kernel<float><<<grid, 256, 0, st>>>((const float *)x, y, N, C, H, W, x_cstride, x_coff,
+                                                         clamp01);
+    else
+        nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, y, N, C, H, W,
+                                                                  x_cstride, x_coff, clamp01);
+    RGBD_LAUNCH_CHECK();
+    return RGBD_OK;
+}

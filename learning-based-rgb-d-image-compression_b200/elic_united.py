@@ -1,0 +1,741 @@
+"""ELIC_united / ELIC_united_R2D — B200-native drop-in for the reference's RGB-D codec classes.
+
+Same constructor, state_dict keys and API surface as the reference
+(models/elic_united.py:15-620, models/elic_united_R2D.py:9-326):
+
+    net = ELIC_united(config=Config(N, M, slice_num, slice_ch, quant), channel=4).eval()
+    net.load_state_dict(ckpt["state_dict"]); net.update(force=True); net.to("cuda")
+    out  = net(rgb, depth)                      # x_hat + likelihoods      (forward,   :234-263)
+    code = net.compress(rgb, depth)             # r_strings / d_strings / shape (compress, :403-427)
+    rec  = net.decompress(code["r_strings"], code["d_strings"], code["shape"])   # (:429-452)
+
+Everything below the API is new: the layer graph is compiled (engine.py) into a static list of
+launches of hand-written sm_100a kernels behind the C-ABI in include/rgbd_b200.h — implicit-GEMM
+convs over NHWC pixels, fused checkerboard/quantise/index kernels and a GPU rANS coder that is
+byte-identical to compressai.ans.  No torch arithmetic runs on the hot path, there is no CPU
+fallback, and the module refuses to run without its CUDA library.
+
+Bitstream layout: per image and modality one y stream covering the 5 channel groups x
+{anchor, non-anchor} in the reference's order (elic_united.py:377-399, utils/ckbd.py:83-105) and one
+z stream; for batch 1 the result is identical to the reference's.  For batch B > 1 the y entry holds
+B per-image strings (the reference would interleave the batch into one stream, which its own
+harness never does: utils/IOutils.py:84-86, config/args.py:66-68).
+"""
+import ctypes
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import lib as L
+from .engine import Builder, PackedConv, View, _DT
+from .entropy_models import EntropyBottleneck, GaussianConditional, get_scale_table
+from .modules import (AnalysisTransform, AttentionBlock, BiSpf, BiSpfSingle, ChannelContextEX,
+                      EntropyParametersEX, HyperAnalysis, HyperSynthesis, ResidualBottleneck,
+                      SynthesisTransform)
+
+RELU, LEAKY, NONE = L.ACT_RELU, L.ACT_LEAKY, L.ACT_NONE
+
+
+class ELIC_united(nn.Module):
+    cross = True  # bidirectional RGB<->depth (Bi-CPT / Bi-CEE); the R2D subclass clears it
+
+    def __init__(self, config, **kwargs):
+        super().__init__()
+        N, M = config.N, config.M
+        self.N, self.M = N, M
+        self.quant = config.quant
+        self.slice_num = config.slice_num
+        self.slice_ch = list(config.slice_ch)
+        assert sum(self.slice_ch) == M and len(self.slice_ch) == self.slice_num
+        sc = self.slice_ch
+        cross = self.cross
+        self.g_a = AnalysisTransform(N, M, cross)
+        self.g_s = SynthesisTransform(N, M, cross)
+        self.h_a = HyperAnalysis(N, M)
+        self.h_s = HyperSynthesis(N, M, cross)
+
+        def local():
+            return nn.ModuleList(nn.Conv2d(c, 2 * c, 5, 1, 2) for c in sc)
+
+        self.rgb_local_context = local()
+        self.rgb_local_context_anchor_with_nonanchor = local()
+        self.depth_local_context = local()
+        self.rgb_channel_context = nn.ModuleList(
+            ChannelContextEX(sum(sc[:i]), sc[i] * 2) if i else None for i in range(self.slice_num))
+        self.depth_channel_context = nn.ModuleList(
+            ChannelContextEX(sum(sc[:i]), sc[i] * 2) if i else None for i in range(self.slice_num))
+        # context widths: hyper (2M per modality) + channel ctx (2g per modality, idx > 0) + locals
+        rh = 4 * M if cross else 2 * M        # hyper channels the rgb branch sees
+        rc = 4 if cross else 2                # channel-ctx multiples of g for rgb
+        self.rgb_entropy_parameters_anchor = nn.ModuleList(
+            EntropyParametersEX(rh + (rc * c if i else 0), 2 * c) for i, c in enumerate(sc))
+        self.depth_entropy_parameters_anchor = nn.ModuleList(
+            EntropyParametersEX(4 * M + 2 * c + (4 * c if i else 0), 2 * c) for i, c in enumerate(sc))
+        rl = 4 if cross else 2                # local-ctx channels for rgb non-anchor
+        self.rgb_entropy_parameters_nonanchor = nn.ModuleList(
+            EntropyParametersEX(rh + rl * c + (rc * c if i else 0), 2 * c) for i, c in enumerate(sc))
+        self.depth_entropy_parameters_nonanchor = nn.ModuleList(
+            EntropyParametersEX(4 * M + 4 * c + (4 * c if i else 0), 2 * c) for i, c in enumerate(sc))
+
+        self.entropy_bottleneck = None
+        self.rgb_entropy_bottleneck = EntropyBottleneck(N)
+        self.depth_entropy_bottleneck = EntropyBottleneck(N)
+        self.gaussianConditional = None
+        self.rgb_gaussian_conditional = GaussianConditional(None)
+        self.depth_gaussian_conditional = GaussianConditional(None)
+
+        self.precision = kwargs.get("precision", "fp32")   # "fp32" | "bf16"
+        self.use_cuda_graph = kwargs.get("cuda_graph", False)
+        self._packed = None      # id(module) -> PackedConv, rebuilt when weights change
+        self._programs = {}
+        self._aux = {}
+
+    # ------------------------------------------------------------------ reference API
+    def count_parameters(self, only_trainable=False):
+        return sum(p.numel() for p in self.parameters() if p.requires_grad or not only_trainable)
+
+    def aux_loss(self):
+        raise NotImplementedError("training is out of scope of the B200 inference path")
+
+    def update(self, scale_table=None, force=False):
+        """models/elic_united.py:580-586 + CompressionModel.update (priors.py:73-92)."""
+        if scale_table is None:
+            scale_table = get_scale_table()
+        r = self.rgb_gaussian_conditional.update_scale_table(scale_table, force=force)
+        d = self.depth_gaussian_conditional.update_scale_table(scale_table, force=force)
+        eb = False
+        for m in (self.rgb_entropy_bottleneck, self.depth_entropy_bottleneck):
+            eb |= m.update(force=force)
+        self._invalidate()
+        return (r & d) | eb
+
+    def load_state_dict(self, state_dict, strict=True):
+        """Resizes the CDF buffers to the checkpoint's sizes first (models/elic_united.py:588-620,
+        utils/moduleFunc.py:42-88), then a normal strict load."""
+        for name in ("rgb_gaussian_conditional", "depth_gaussian_conditional", "rgb_entropy_bottleneck",
+                     "depth_entropy_bottleneck"):
+            mod = getattr(self, name)
+            bufs = ["_quantized_cdf", "_offset", "_cdf_length"]
+            if name.endswith("gaussian_conditional"):
+                bufs.append("scale_table")
+            for b in bufs:
+                key = f"{name}.{b}"
+                if key in state_dict:
+                    cur = getattr(mod, b)
+                    if cur.numel() == 0 or cur.shape != state_dict[key].shape:
+                        setattr(mod, b, torch.empty(state_dict[key].shape, dtype=cur.dtype, device=cur.device))
+            mod.invalidate()
+        rv = super().load_state_dict(state_dict, strict=strict)
+        self._invalidate()
+        return rv
+
+    def _apply(self, fn, *a, **k):
+        rv = super()._apply(fn, *a, **k)
+        self._invalidate()
+        return rv
+
+    def _invalidate(self):
+        self._packed = None
+        self._programs = {}
+        self._aux = {}
+        for m in (self.rgb_gaussian_conditional, self.depth_gaussian_conditional, self.rgb_entropy_bottleneck,
+                  self.depth_entropy_bottleneck):
+            m.invalidate()
+
+    def set_precision(self, precision):
+        assert precision in ("fp32", "bf16")
+        if precision != self.precision:
+            self.precision = precision
+            self._programs = {}
+
+    # ------------------------------------------------------------------ weights on device
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def act_dtype(self):
+        return torch.float32 if self.precision == "fp32" else torch.bfloat16
+
+    def _pc(self, mod, in_perm=None):
+        if self._packed is None:
+            self._packed = {}
+        key = id(mod)
+        if key not in self._packed:
+            self._packed[key] = PackedConv(mod, self.device, in_perm)
+        return self._packed[key]
+
+    def _dev32(self, key, make):
+        if key not in self._aux:
+            self._aux[key] = make().detach().to(device=self.device, dtype=torch.float32).contiguous()
+        return self._aux[key]
+
+    # ------------------------------------------------------------------ graph pieces
+    def _rb(self, b, m, x, out=None):
+        """ResidualBottleneck (res_blk.py:7-27): x (+skip) + 1x1(relu(3x3(relu(1x1 x))))"""
+        t1 = b.conv(self._pc(m.branch[0]), x, act=RELU)
+        t2 = b.conv(self._pc(m.branch[2]), t1, act=RELU)
+        b.release(t1)
+        if m.skip is not None:
+            idn = b.conv(self._pc(m.skip), x, out=out)
+            y = b.conv(self._pc(m.branch[4]), t2, out=idn, res=idn)
+        else:
+            y = b.conv(self._pc(m.branch[4]), t2, out=out, res=x)
+        b.release(t2)
+        return y
+
+    def _ru(self, b, m, x):
+        """AttentionBlock.ResidualUnit (layers.py:178-197): relu(x + conv(x))"""
+        t1 = b.conv(self._pc(m.conv[0]), x, act=RELU)
+        t2 = b.conv(self._pc(m.conv[2]), t1, act=RELU)
+        b.release(t1)
+        y = b.conv(self._pc(m.conv[4]), t2, res=x, act=RELU)
+        b.release(t2)
+        return y
+
+    def _attention(self, b, m, x, out=None, out_dtype=None):
+        """AttentionBlock (layers.py:162-213): x + a(x) * sigmoid(b(x))"""
+        a = x
+        for i in range(3):
+            n = self._ru(b, m.conv_a[i], a)
+            if a is not x:
+                b.release(a)
+            a = n
+        t = x
+        for i in range(3):
+            n = self._ru(b, m.conv_b[i], t)
+            if t is not x:
+                b.release(t)
+            t = n
+        y = b.conv(self._pc(m.conv_b[3]), t, out=out, epi=L.EPI_GATE, mul=a, res=x, out_dtype=out_dtype)
+        b.release(a, t)
+        return y
+
+    def _esa(self, b, m, x, out):
+        """ESA (attention.py:70-97): x * sigmoid(conv4(upsample(small path) + conv_f(conv1 x)))"""
+        c1_ = b.conv(self._pc(m.conv1), x)
+        c1 = b.conv(self._pc(m.conv2), c1_)
+        vmax = b.maxpool7s3(c1)
+        b.release(c1)
+        vr = b.conv(self._pc(m.conv_max), vmax, act=RELU)
+        b.release(vmax)
+        c3 = b.conv(self._pc(m.conv3), vr, act=RELU)
+        b.release(vr)
+        c3b = b.conv(self._pc(m.conv3_), c3)
+        b.release(c3)
+        s = b.conv(self._pc(m.conv_f), c1_, epi=L.EPI_BILERP, res=c3b)
+        b.release(c1_, c3b)
+        y = b.conv(self._pc(m.conv4), s, out=out, epi=L.EPI_GATE, mul=x)
+        b.release(s)
+        return y
+
+    def _bispf(self, b, m, rgb, depth, rgb_out, depth_out):
+        """bi_spf / bi_spf_single (attention.py:14-48). rgb/depth: N-channel views; *_out: the
+        N-channel slot after them in the 2N-wide concat buffer (rgb_out None for the single form)."""
+        Nh = m.r_ext.out_channels
+        e = b.alloc(rgb.N, rgb.H, rgb.W, 3 * Nh)          # [r | d | r]
+        b.conv(self._pc(m.r_ext), rgb, out=e.sub(0, Nh), act=RELU, y2=e.sub(2 * Nh, Nh))
+        b.conv(self._pc(m.d_ext), depth, out=e.sub(Nh, Nh), act=RELU)
+        if rgb_out is not None:
+            self._esa(b, m.r_esa, e.sub(0, 2 * Nh), rgb_out)       # ESA(cat(r, d))
+        self._esa(b, m.d_esa, e.sub(Nh, 2 * Nh), depth_out)        # ESA(cat(d, r))
+        b.release(e)
+
+    def _transform(self, b, rgb_seq, depth_seq, r, d, final_dtype=None):
+        """Walks the paired nn.Sequential of g_a / g_s (analysis.py:168-181, synthesis.py:171-184)."""
+        n = len(rgb_seq)
+        N = self.N
+        for i in range(n):
+            rm, dm = rgb_seq[i], depth_seq[i]
+            last = i == n - 1
+            # does a bi_spf follow? then this stage writes into the first half of a 2N buffer
+            nxt = rgb_seq[i + 1] if i + 1 < n else None
+            feeds_spf = isinstance(nxt, BiSpfSingle)
+            if isinstance(rm, BiSpfSingle):
+                # r, d are views [0:N] of 2N-wide buffers (depth always; rgb only when bidirectional)
+                if isinstance(rm, BiSpf):
+                    self._bispf(b, rm, r, d, View(r.buf, N, N), View(d.buf, N, N))
+                    r = View(r.buf)
+                else:
+                    self._bispf(b, rm, r, d, None, View(d.buf, N, N))
+                d = View(d.buf)
+                continue
+
+            def out_for(is_rgb, Hh, Ww, Cc):
+                wide = feeds_spf and (self.cross or not is_rgb)
+                if wide:
+                    return View(b.alloc(r.N, Hh, Ww, 2 * Cc).buf, 0, Cc)
+                return None
+
+            def step(mod, x, is_rgb):
+                if isinstance(mod, (nn.Conv2d, nn.ConvTranspose2d)):
+                    pc = self._pc(mod)
+                    Ho, Wo, _ = pc.launches(x.H, x.W)
+                    return b.conv(pc, x, out=out_for(is_rgb, Ho, Wo, pc.Cout),
+                                  out_dtype=final_dtype if last else None)
+                if isinstance(mod, ResidualBottleneck):
+                    return self._rb(b, mod, x, out=out_for(is_rgb, x.H, x.W, mod.branch[4].out_channels))
+                if isinstance(mod, AttentionBlock):
+                    return self._attention(b, mod, x, out=out_for(is_rgb, x.H, x.W, x.C),
+                                           out_dtype=final_dtype if last else None)
+                raise TypeError(type(mod))
+
+            nr, nd = step(rm, r, True), step(dm, d, False)
+            if i > 0:
+                b.release(r, d)
+            r, d = nr, nd
+        return r, d
+
+    def _h_a(self, b, y_r, y_d):
+        outs = []
+        for seq, y in ((self.h_a.rgb_reduction, y_r), (self.h_a.depth_reduction, y_d)):
+            t1 = b.conv(self._pc(seq[0]), y, act=RELU)
+            t2 = b.conv(self._pc(seq[2]), t1, act=RELU)
+            z = b.conv(self._pc(seq[4]), t2, out_dtype=torch.float32)
+            b.release(t1, t2)
+            outs.append(z)
+        return outs
+
+    def _se_weights(self, se, perm=None):
+        w1 = self._dev32(("se1", id(se)), lambda: se.fc[0].weight if perm is None else se.fc[0].weight[:, perm])
+        w2 = self._dev32(("se2", id(se)), lambda: se.fc[2].weight if perm is None else se.fc[2].weight[perm, :])
+        return w1, w2
+
+    def _hyper_block(self, b, m, x, out=None, y2=None):
+        """hyper_transform_block[_single] (synthesis.py:345-380): deconv(SE(x)) (+LeakyReLU)"""
+        w1, w2 = self._se_weights(m.se)
+        s = b.se_scale(x, w1, w2, plus_one=False)
+        return b.conv(self._pc(m.deconv), x, out=out, y2=y2, in_scale=s, act=NONE if m.is_last else LEAKY)
+
+    def _h_s(self, b, zcat, ctx_r, ctx_d):
+        """HyperSynthesisEXcross / EXSingle (synthesis.py:305-343).  zcat = [z_r | z_d | z_r] so both
+        cat orders are views; the last stage writes straight into the context buffers."""
+        Nz, M = self.N, self.M
+        hs = self.h_s
+        B, h, w = zcat.N, zcat.H, zcat.W
+        c1 = b.alloc(B, 2 * h, 2 * w, 3 * M)            # [r1 | d1 | r1]
+        c2 = b.alloc(B, 4 * h, 4 * w, 3 * (M * 3 // 2))  # [r2 | d2 | r2]
+        M2 = M * 3 // 2
+        if self.cross:
+            self._hyper_block(b, hs.r_h_s1, zcat.sub(0, 2 * Nz), out=c1.sub(0, M), y2=c1.sub(2 * M, M))
+            self._hyper_block(b, hs.d_h_s1, zcat.sub(Nz, 2 * Nz), out=c1.sub(M, M))
+            self._hyper_block(b, hs.r_h_s2, c1.sub(0, 2 * M), out=c2.sub(0, M2), y2=c2.sub(2 * M2, M2))
+            self._hyper_block(b, hs.d_h_s2, c1.sub(M, 2 * M), out=c2.sub(M2, M2))
+            self._hyper_block(b, hs.r_h_s3, c2.sub(0, 2 * M2), out=ctx_r)
+            self._hyper_block(b, hs.d_h_s3, c2.sub(M2, 2 * M2), out=ctx_d)
+        else:
+            self._hyper_block(b, hs.r_h_s1, zcat.sub(0, Nz), out=c1.sub(0, M), y2=c1.sub(2 * M, M))
+            self._hyper_block(b, hs.d_h_s1, zcat.sub(Nz, 2 * Nz), out=c1.sub(M, M))
+            self._hyper_block(b, hs.r_h_s2, c1.sub(0, M), out=c2.sub(0, M2), y2=c2.sub(2 * M2, M2))
+            self._hyper_block(b, hs.d_h_s2, c1.sub(M, 2 * M), out=c2.sub(M2, M2))
+            self._hyper_block(b, hs.r_h_s3, c2.sub(0, M2), out=ctx_r)
+            self._hyper_block(b, hs.d_h_s3, c2.sub(M2, 2 * M2), out=ctx_d)
+        b.release(c1, c2)
+
+    def _dup(self, b, src, dst):
+        b.op("rgbd_copy_view", src.ptr(), dst.ptr(), _DT[src.dtype], src.N * src.H * src.W, src.C, src.cstride,
+             src.coff, dst.cstride, dst.coff)
+
+    # ------------------------------------------------------------------ Bi-CEE context model
+    def _ctx_layout(self, idx):
+        """Channel layout of the shared context buffer for slice idx.
+        ours:  [hyper_r 2M | hyper_d 2M | ch_r 2g | ch_d 2g | loc_r 2g | loc_d 2g]   (ch_* only idx>0)
+        Returns offsets and, per EntropyParametersEX, (width, perm) where perm[j] = index into the
+        reference's torch.cat order (elic_united.py:288,302,317,333) of our channel j."""
+        M, g = self.M, self.slice_ch[idx]
+        has_ch = idx > 0
+        o = {"hyper_r": 0, "hyper_d": 2 * M}
+        p = 4 * M
+        if has_ch:
+            o["ch_r"], o["ch_d"] = p, p + 2 * g
+            p += 4 * g
+        o["loc_r"], o["loc_d"] = p, p + 2 * g
+        o["end"] = p + 4 * g
+
+        def perm(ref_order, ours):
+            start, q = {}, 0
+            for name, width in ref_order:
+                start[name] = q
+                q += width
+            idxs = []
+            for name, width in ours:
+                idxs.extend(range(start[name], start[name] + width))
+            assert len(idxs) == q
+            return torch.tensor(idxs, dtype=torch.long)
+
+        base = [("hyper_r", 2 * M), ("hyper_d", 2 * M)] + ([("ch_r", 2 * g), ("ch_d", 2 * g)] if has_ch else [])
+        lr, ld = ("loc_r", 2 * g), ("loc_d", 2 * g)
+        plans = {
+            "r_anchor": perm(base, base),
+            "d_anchor": perm([lr] + base, base + [lr]),
+            "r_nonanchor": perm([lr, ld] + base, base + [lr, ld]),
+            "d_nonanchor": perm([lr, ld] + base, base + [lr, ld]),
+        }
+        return o, plans
+
+    def _ep(self, b, m, x, perm, out):
+        """EntropyParametersEX (entropy.py:56-78): fusion(x + se(x)) -> fp32 (scales | means)"""
+        w1, w2 = self._se_weights(m.se, perm)
+        s = b.se_scale(x, w1, w2, plus_one=True)
+        t1 = b.conv(self._pc(m.fusion[0], in_perm=perm), x, in_scale=s, act=RELU)
+        t2 = b.conv(self._pc(m.fusion[2]), t1, act=RELU)
+        b.release(t1)
+        y = b.conv(self._pc(m.fusion[4]), t2, out=out)
+        b.release(t2)
+        return y
+
+    def _channel_ctx(self, b, m, x, out):
+        t1 = b.conv(self._pc(m.fushion[0]), x, act=RELU)
+        t2 = b.conv(self._pc(m.fushion[2]), t1, act=RELU)
+        b.release(t1)
+        b.conv(self._pc(m.fushion[4]), t2, out=out)
+        b.release(t2)
+
+    def _context_chain(self, b, ctx, yhat_r, yhat_d, code_step):
+        """The 20-stage serial chain (elic_united.py:265-348 / 454-541).  code_step(mod, idx, parity,
+        params_view, g, coff) emits the kernels that turn Gaussian params into y_hat at the parity
+        sites (quantise in the encoder, rANS-decode in the decoder, ste+likelihood in forward)."""
+        assert self.cross, "R2D context chain is built by the subclass"
+        for idx, g in enumerate(self.slice_ch):
+            coff = sum(self.slice_ch[:idx])
+            o, perms = self._ctx_layout(idx)
+            params = b.alloc(ctx.N, ctx.H, ctx.W, 2 * g, torch.float32)
+            if idx > 0:
+                self._channel_ctx(b, self.rgb_channel_context[idx], yhat_r.sub(0, coff), ctx.sub(o["ch_r"], 2 * g))
+                self._channel_ctx(b, self.depth_channel_context[idx], yhat_d.sub(0, coff), ctx.sub(o["ch_d"], 2 * g))
+            pre = o["loc_r"]
+            # (1) rgb anchor
+            self._ep(b, self.rgb_entropy_parameters_anchor[idx], ctx.sub(0, pre), perms["r_anchor"], params)
+            code_step("r", idx, 0, params, g, coff)
+            b.conv(self._pc(self.rgb_local_context[idx]), yhat_r.sub(coff, g), out=ctx.sub(o["loc_r"], 2 * g))
+            # (2) depth anchor
+            self._ep(b, self.depth_entropy_parameters_anchor[idx], ctx.sub(0, pre + 2 * g), perms["d_anchor"], params)
+            code_step("d", idx, 0, params, g, coff)
+            b.conv(self._pc(self.depth_local_context[idx]), yhat_d.sub(coff, g), out=ctx.sub(o["loc_d"], 2 * g))
+            # (3) rgb non-anchor
+            self._ep(b, self.rgb_entropy_parameters_nonanchor[idx], ctx.sub(0, pre + 4 * g), perms["r_nonanchor"], params)
+            code_step("r", idx, 1, params, g, coff)
+            b.conv(self._pc(self.rgb_local_context_anchor_with_nonanchor[idx]), yhat_r.sub(coff, g),
+                   out=ctx.sub(o["loc_r"], 2 * g))
+            # (4) depth non-anchor
+            self._ep(b, self.depth_entropy_parameters_nonanchor[idx], ctx.sub(0, pre + 4 * g), perms["d_nonanchor"], params)
+            code_step("d", idx, 1, params, g, coff)
+            b.release(params)
+
+    # ------------------------------------------------------------------ programs
+    def _gc(self, which):
+        return self.rgb_gaussian_conditional if which == "r" else self.depth_gaussian_conditional
+
+    def _eb(self, which):
+        return self.rgb_entropy_bottleneck if which == "r" else self.depth_entropy_bottleneck
+
+    def _chunk_offsets(self, h, w):
+        """Symbol offsets of the 10 chunks inside one image's y stream."""
+        offs, p = {}, 0
+        for idx, g in enumerate(self.slice_ch):
+            for parity in (0, 1):
+                offs[(idx, parity)] = p
+                p += g * h * (w // 2)
+        return offs, p
+
+    def _common_front(self, b, B, H, W):
+        """image -> g_a -> h_a. Returns io views."""
+        p = b.prog
+        x_r = b.alloc(B, H, W, 3)
+        x_d = b.alloc(B, H, W, 1)
+        in_r = b.raw((B, 3, H, W), torch.float32)
+        in_d = b.raw((B, 1, H, W), torch.float32)
+        p.io["rgb"], p.io["depth"] = in_r, in_d
+        b.op("rgbd_nchw_to_nhwc", in_r.data_ptr(), x_r.ptr(), _DT[x_r.dtype], B, 3, H, W, 3, 0)
+        b.op("rgbd_nchw_to_nhwc", in_d.data_ptr(), x_d.ptr(), _DT[x_d.dtype], B, 1, H, W, 1, 0)
+        y_r, y_d = self._transform(b, self.g_a.rgb_analysis_transform, self.g_a.depth_analysis_transform,
+                                   x_r, x_d, final_dtype=torch.float32)
+        z_r, z_d = self._h_a(b, y_r, y_d)
+        return y_r, y_d, z_r, z_d
+
+    def _tables(self, which_model, which):
+        m = self._gc(which) if which_model == "gc" else self._eb(which)
+        return m.device_tables(self.device)
+
+    def _build_encoder(self, B, H, W):
+        b = Builder(self.device, self.act_dtype)
+        p = b.prog
+        y_r, y_d, z_r, z_d = self._common_front(b, B, H, W)
+        h, w = y_r.H, y_r.W
+        hz, wz = z_r.H, z_r.W
+        Nz, M = self.N, self.M
+        nz = Nz * hz * wz
+        zcat = b.alloc(B, hz, wz, 3 * Nz)
+        ys = {"r": y_r, "d": y_d}
+        zs = {"r": z_r, "d": z_d}
+        offs, ny = self._chunk_offsets(h, w)
+        st = {}
+        for which in ("r", "d"):
+            eb = self._eb(which)
+            med = self._dev32(("med", which), eb.medians)
+            s = dict(
+                zsym=b.raw((B, nz), torch.int32), zidx=b.raw((B, nz), torch.uint8),
+                ysym=b.raw((B, ny), torch.int32), yidx=b.raw((B, ny), torch.uint8),
+                zcap=nz + nz // 2 + 64, ycap=ny + ny // 2 + 64)
+            s["zout"] = b.raw((B, s["zcap"]), torch.int32)
+            s["yout"] = b.raw((B, s["ycap"]), torch.int32)
+            s["znw"] = b.raw((B,), torch.int32)
+            s["ynw"] = b.raw((B,), torch.int32)
+            st[which] = s
+            zh = zcat.sub(0 if which == "r" else Nz, Nz)
+            b.op("rgbd_eb_quantize", zs[which].ptr(), zs[which].cstride, B, hz * wz, Nz, med.data_ptr(),
+                 s["zsym"].data_ptr(), s["zidx"].data_ptr(), zh.ptr(), _DT[zh.dtype], zh.cstride, zh.coff)
+            t = self._tables("eb", which)
+            b.op("rgbd_rans_encode", s["zsym"].data_ptr(), s["zidx"].data_ptr(), nz, nz, B, ctypes.byref(t.struct),
+                 s["zout"].data_ptr(), s["zcap"], s["znw"].data_ptr())
+            p.keep.append(t)
+        self._dup(b, zcat.sub(0, Nz), zcat.sub(2 * Nz, Nz))
+        ctx = b.alloc(B, h, w, 4 * M + 8 * max(self.slice_ch))
+        self._h_s(b, zcat, ctx.sub(0, 2 * M), ctx.sub(2 * M, 2 * M))
+        yhat = {"r": b.alloc(B, h, w, M, zero=True), "d": b.alloc(B, h, w, M, zero=True)}
+        for which in ("r", "d"):
+            t = yhat[which].buf
+            b.op("rgbd_zero", t.data_ptr(), t.numel() * t.element_size())
+        table = {k: self._dev32(("scale_table", k), lambda k=k: self._gc(k).scale_table) for k in ("r", "d")}
+        bound = {k: float(self._gc(k).lower_bound_scale.bound) for k in ("r", "d")}
+
+        def code_step(which, idx, parity, params, g, coff):
+            s = st[which]
+            b.op("rgbd_ckbd_quantize_index", ys[which].ptr(), ys[which].cstride, ys[which].coff + coff,
+                 params.ptr(), table[which].data_ptr(), table[which].numel(), bound[which], B, h, w, g, parity,
+                 s["ysym"].data_ptr(), s["yidx"].data_ptr(), ny, offs[(idx, parity)],
+                 yhat[which].ptr(), _DT[yhat[which].dtype], yhat[which].cstride, coff)
+
+        self._context_chain(b, ctx, yhat["r"], yhat["d"], code_step)
+        for which in ("r", "d"):
+            s = st[which]
+            t = self._tables("gc", which)
+            b.op("rgbd_rans_encode", s["ysym"].data_ptr(), s["yidx"].data_ptr(), ny, ny, B, ctypes.byref(t.struct),
+                 s["yout"].data_ptr(), s["ycap"], s["ynw"].data_ptr())
+            p.keep.append(t)
+        p.io.update(st=st, shape=(hz, wz), y=ys, z=zs, yhat=yhat, ny=ny, nz=nz)
+        return p
+
+    def _build_decoder(self, B, hz, wz):
+        b = Builder(self.device, self.act_dtype)
+        p = b.prog
+        Nz, M = self.N, self.M
+        h, w = hz * 4, wz * 4
+        H, W = h * 16, w * 16
+        nz = Nz * hz * wz
+        offs, ny = self._chunk_offsets(h, w)
+        zcat = b.alloc(B, hz, wz, 3 * Nz)
+        # stream table: 4*B streams in the order [z_r | z_d | y_r | y_d], each B long
+        words_cap = 2 * B * ((nz + nz // 2 + 64) + (ny + ny // 2 + 64))
+        words = b.raw((words_cap,), torch.int32)
+        word_off = b.raw((4 * B,), torch.int64)
+        word_len = b.raw((4 * B,), torch.int64)
+        state = b.raw((4 * B, 2), torch.int64)
+        p.io.update(words=words, word_off=word_off, word_len=word_len, words_cap=words_cap)
+        b.op("rgbd_rans_decode_init", words.data_ptr(), word_off.data_ptr(), 4 * B, state.data_ptr())
+        st = {}
+        for k, which in enumerate(("r", "d")):
+            eb = self._eb(which)
+            med = self._dev32(("med", which), eb.medians)
+            s = dict(zsym=b.raw((B, nz), torch.int32), zidx=b.raw((B, nz), torch.uint8),
+                     ysym=b.raw((B, ny), torch.int32), yidx=b.raw((B, ny), torch.uint8),
+                     zslot=k * B, yslot=(2 + k) * B)
+            st[which] = s
+            chan = torch.arange(Nz, device=self.device, dtype=torch.uint8).repeat_interleave(hz * wz).repeat(B, 1)
+            s["zidx"].copy_(chan)   # EntropyBottleneck._build_indexes (entropy_models.py:430-435)
+            t = self._tables("eb", which)
+            b.op("rgbd_rans_decode_chunk", words.data_ptr(), word_off[s["zslot"]:].data_ptr(),
+                 word_len[s["zslot"]:].data_ptr(), B, state[s["zslot"]:].data_ptr(), s["zidx"].data_ptr(),
+                 s["zsym"].data_ptr(), nz, 0, nz, ctypes.byref(t.struct))
+            p.keep.append(t)
+            zh = zcat.sub(0 if which == "r" else Nz, Nz)
+            b.op("rgbd_eb_dequantize", s["zsym"].data_ptr(), B, hz * wz, Nz, med.data_ptr(), zh.ptr(),
+                 _DT[zh.dtype], zh.cstride, zh.coff)
+        self._dup(b, zcat.sub(0, Nz), zcat.sub(2 * Nz, Nz))
+        ctx = b.alloc(B, h, w, 4 * M + 8 * max(self.slice_ch))
+        self._h_s(b, zcat, ctx.sub(0, 2 * M), ctx.sub(2 * M, 2 * M))
+        yhat = {"r": b.alloc(B, h, w, M, zero=True), "d": b.alloc(B, h, w, M, zero=True)}
+        for which in ("r", "d"):
+            t = yhat[which].buf
+            b.op("rgbd_zero", t.data_ptr(), t.numel() * t.element_size())
+        table = {k: self._dev32(("scale_table", k), lambda k=k: self._gc(k).scale_table) for k in ("r", "d")}
+        bound = {k: float(self._gc(k).lower_bound_scale.bound) for k in ("r", "d")}
+
+        def code_step(which, idx, parity, params, g, coff):
+            s = st[which]
+            n = g * h * (w // 2)
+            off = offs[(idx, parity)]
+            t = self._tables("gc", which)
+            b.op("rgbd_ckbd_index", params.ptr(), table[which].data_ptr(), table[which].numel(), bound[which],
+                 B, h, w, g, parity, s["yidx"].data_ptr(), ny, off)
+            b.op("rgbd_rans_decode_chunk", words.data_ptr(), word_off[s["yslot"]:].data_ptr(),
+                 word_len[s["yslot"]:].data_ptr(), B, state[s["yslot"]:].data_ptr(), s["yidx"].data_ptr(),
+                 s["ysym"].data_ptr(), ny, off, n, ctypes.byref(t.struct))
+            b.op("rgbd_ckbd_dequant_scatter", s["ysym"].data_ptr(), ny, off, params.ptr(), B, h, w, g, parity,
+                 yhat[which].ptr(), _DT[yhat[which].dtype], yhat[which].cstride, coff)
+            p.keep.append(t)
+
+        self._context_chain(b, ctx, yhat["r"], yhat["d"], code_step)
+        x_r, x_d = self._transform(b, self.g_s.rgb_synthesis_transform, self.g_s.depth_synthesis_transform,
+                                   yhat["r"], yhat["d"])
+        out_r = b.raw((B, 3, H, W), torch.float32)
+        out_d = b.raw((B, 1, H, W), torch.float32)
+        b.op("rgbd_nhwc_to_nchw", x_r.ptr(), _DT[x_r.dtype], out_r.data_ptr(), B, 3, H, W, x_r.cstride, x_r.coff, 1)
+        b.op("rgbd_nhwc_to_nchw", x_d.ptr(), _DT[x_d.dtype], out_d.data_ptr(), B, 1, H, W, x_d.cstride, x_d.coff, 1)
+        p.io.update(st=st, out_r=out_r, out_d=out_d, yhat=yhat, ny=ny, nz=nz)
+        return p
+
+    def _build_forward(self, B, H, W):
+        b = Builder(self.device, self.act_dtype)
+        p = b.prog
+        y_r, y_d, z_r, z_d = self._common_front(b, B, H, W)
+        h, w = y_r.H, y_r.W
+        hz, wz = z_r.H, z_r.W
+        Nz, M = self.N, self.M
+        zcat = b.alloc(B, hz, wz, 3 * Nz)
+        ys = {"r": y_r, "d": y_d}
+        zs = {"r": z_r, "d": z_d}
+        lik = {}
+        for which in ("r", "d"):
+            eb = self._eb(which)
+            ebp = eb.packed_params(self.device)
+            p.keep.append(ebp)
+            lz = b.raw((B, Nz, hz, wz), torch.float32)
+            ly = b.raw((B, M, h, w), torch.float32)
+            lik[which] = (ly, lz)
+            zh = zcat.sub(0 if which == "r" else Nz, Nz)
+            b.op("rgbd_eb_likelihood", zs[which].ptr(), zs[which].cstride, B, hz * wz, Nz, ebp.data_ptr(),
+                 eb.likelihood_bound, zh.ptr(), _DT[zh.dtype], zh.cstride, zh.coff, lz.data_ptr())
+        self._dup(b, zcat.sub(0, Nz), zcat.sub(2 * Nz, Nz))
+        ctx = b.alloc(B, h, w, 4 * M + 8 * max(self.slice_ch))
+        self._h_s(b, zcat, ctx.sub(0, 2 * M), ctx.sub(2 * M, 2 * M))
+        yhat = {"r": b.alloc(B, h, w, M, zero=True), "d": b.alloc(B, h, w, M, zero=True)}
+        for which in ("r", "d"):
+            t = yhat[which].buf
+            b.op("rgbd_zero", t.data_ptr(), t.numel() * t.element_size())
+        bound = {k: float(self._gc(k).lower_bound_scale.bound) for k in ("r", "d")}
+
+        def code_step(which, idx, parity, params, g, coff):
+            gc = self._gc(which)
+            b.op("rgbd_ckbd_ste_likelihood", ys[which].ptr(), ys[which].cstride, ys[which].coff + coff,
+                 params.ptr(), bound[which], gc.likelihood_bound, B, h, w, g, parity, yhat[which].ptr(),
+                 _DT[yhat[which].dtype], yhat[which].cstride, coff, lik[which][0].data_ptr(), M, coff)
+
+        self._context_chain(b, ctx, yhat["r"], yhat["d"], code_step)
+        x_r, x_d = self._transform(b, self.g_s.rgb_synthesis_transform, self.g_s.depth_synthesis_transform,
+                                   yhat["r"], yhat["d"])
+        out_r = b.raw((B, 3, H, W), torch.float32)
+        out_d = b.raw((B, 1, H, W), torch.float32)
+        b.op("rgbd_nhwc_to_nchw", x_r.ptr(), _DT[x_r.dtype], out_r.data_ptr(), B, 3, H, W, x_r.cstride, x_r.coff, 0)
+        b.op("rgbd_nhwc_to_nchw", x_d.ptr(), _DT[x_d.dtype], out_d.data_ptr(), B, 1, H, W, x_d.cstride, x_d.coff, 0)
+        p.io.update(out_r=out_r, out_d=out_d, lik=lik, y=ys, z=zs, yhat=yhat)
+        return p
+
+    def _program(self, kind, *dims):
+        key = (kind, self.precision) + tuple(dims)
+        if key not in self._programs:
+            self._require_cuda()
+            with torch.cuda.device(self.device), torch.no_grad():
+                self._programs[key] = getattr(self, "_build_" + kind)(*dims)
+        return self._programs[key]
+
+    def _require_cuda(self):
+        L.load()  # raises if the CUDA extension is missing — there is no fallback path
+        if self.device.type != "cuda":
+            raise L.RgbdError("ELIC_united runs on a CUDA device only (no CPU fallback); call .to('cuda')")
+        if self.rgb_gaussian_conditional.quantized_cdf.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+
+    def _check_inputs(self, rgb, depth):
+        if rgb.dim() != 4 or depth.dim() != 4 or rgb.shape[1] != 3 or depth.shape[1] != 1:
+            raise ValueError("expected rgb [B,3,H,W] and depth [B,1,H,W]")
+        if rgb.shape[0] != depth.shape[0] or rgb.shape[2:] != depth.shape[2:]:
+            raise ValueError("rgb and depth must have the same batch and spatial size")
+        if rgb.shape[2] % 64 or rgb.shape[3] % 64:
+            raise ValueError("H and W must be multiples of 64 (pad first, dataset/utils.py:58-67)")
+        if rgb.shape[2] < 128 or rgb.shape[3] < 128:
+            raise ValueError("H and W must be >= 128 (ESA max_pool2d(7, 3) on the 1/8-scale map)")
+
+    # ------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def forward(self, rgb, depth):
+        self._check_inputs(rgb, depth)
+        B, _, H, W = rgb.shape
+        p = self._program("forward", B, H, W)
+        with torch.cuda.device(self.device):
+            p.io["rgb"].copy_(rgb)
+            p.io["depth"].copy_(depth)
+            p.run(self.use_cuda_graph)
+        lik = p.io["lik"]
+        return {
+            "x_hat": {"r": p.io["out_r"].clone(), "d": p.io["out_d"].clone()},
+            "r_likelihoods": {"y": lik["r"][0].clone(), "z": lik["r"][1].clone()},
+            "d_likelihoods": {"y": lik["d"][0].clone(), "z": lik["d"][1].clone()},
+        }
+
+    @torch.no_grad()
+    def compress(self, rgb, depth):
+        self._check_inputs(rgb, depth)
+        B, _, H, W = rgb.shape
+        p = self._program("encoder", B, H, W)
+        with torch.cuda.device(self.device):
+            p.io["rgb"].copy_(rgb)
+            p.io["depth"].copy_(depth)
+            p.run(self.use_cuda_graph)
+            strings = self._collect_strings(p, B)
+        return {"r_strings": [strings["ry"], strings["rz"]], "d_strings": [strings["dy"], strings["dz"]],
+                "shape": torch.Size(p.io["shape"])}
+
+    def _collect_strings(self, p, B):
+        """One small D2H for the word counts, one packed D2H for all stream tails."""
+        st = p.io["st"]
+        counts = torch.stack([st["r"]["ynw"], st["r"]["znw"], st["d"]["ynw"], st["d"]["znw"]]).cpu().numpy()
+        if (counts < 0).any():
+            raise L.RgbdError("rANS output buffer overflow (stream longer than 48 bits/symbol)")
+        pieces, meta = [], []
+        for row, (which, kind) in enumerate((("r", "y"), ("r", "z"), ("d", "y"), ("d", "z"))):
+            out, cap = st[which][kind + "out"], st[which][kind + "cap"]
+            for i in range(B):
+                n = int(counts[row, i])
+                pieces.append(out[i, cap - n:])
+                meta.append((which + kind, n))
+        host = torch.cat(pieces).cpu().numpy()
+        res = {"ry": [], "rz": [], "dy": [], "dz": []}
+        pos = 0
+        for key, n in meta:
+            res[key].append(host[pos:pos + n].tobytes())
+            pos += n
+        return res
+
+    @torch.no_grad()
+    def decompress(self, rgb_strings, depth_strings, shape):
+        self._require_cuda()
+        torch.cuda.synchronize(self.device)
+        t0 = time.process_time()
+        rz, dz = list(rgb_strings[1]), list(depth_strings[1])
+        B = len(rz)
+        ry, dy = list(rgb_strings[0]), list(depth_strings[0])
+        if len(ry) != B or len(dy) != B or len(dz) != B:
+            raise ValueError(f"expected {B} y strings per modality (one per image), got {len(ry)} / {len(dy)}")
+        hz, wz = int(shape[0]), int(shape[1])
+        p = self._program("decoder", B, hz, wz)
+        streams = rz + dz + ry + dy
+        lens = np.array([len(s) // 4 for s in streams], dtype=np.int64)
+        if any(len(s) % 4 or len(s) < 8 for s in streams):
+            raise ValueError("corrupt stream: rANS payloads are whole 32-bit words, at least two")
+        offs = np.zeros_like(lens)
+        offs[1:] = np.cumsum(lens[:-1])
+        total = int(lens.sum())
+        if total > p.io["words_cap"]:
+            raise ValueError("streams larger than the decoder's word buffer")
+        blob = np.frombuffer(b"".join(streams), dtype=np.int32)
+        with torch.cuda.device(self.device):
+            p.io["words"][:total].copy_(torch.from_numpy(blob.copy()))
+            p.io["word_off"].copy_(torch.from_numpy(offs))
+            p.io["word_len"].copy_(torch.from_numpy(lens))
+            p.run(self.use_cuda_graph)
+            out_r, out_d = p.io["out_r"].clone(), p.io["out_d"].clone()
+            torch.cuda.synchronize(self.device)
+        return {"x_hat": {"r": out_r, "d": out_d}, "cost_time": time.process_time() - t0}

@@ -1,0 +1,237 @@
+"""Launch-plan compiler: turns the ELIC_united layer graph into a static list of C-ABI
+kernel launches over pre-allocated NHWC buffers in HBM.
+
+A `Program` is built once per (kind, batch, H, W, precision): buffer addresses never change,
+so the launch list can be replayed as-is or captured into a CUDA graph.  torch is used for
+device memory and streams only; every arithmetic op on the path is one of our kernels.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+_DT = {torch.float32: L.DT_F32, torch.bfloat16: L.DT_BF16}
+
+
+class View:
+    """Channel-slice view [coff, coff+C) of an NHWC buffer."""
+
+    __slots__ = ("buf", "coff", "C")
+
+    def __init__(self, buf, coff=0, C=None):
+        self.buf = buf
+        self.coff = int(coff)
+        self.C = int(buf.shape[3] - coff if C is None else C)
+        assert 0 <= self.coff and self.coff + self.C <= buf.shape[3], (buf.shape, coff, C)
+
+    N = property(lambda s: s.buf.shape[0])
+    H = property(lambda s: s.buf.shape[1])
+    W = property(lambda s: s.buf.shape[2])
+    cstride = property(lambda s: s.buf.shape[3])
+    dtype = property(lambda s: s.buf.dtype)
+
+    def ptr(self):
+        return self.buf.data_ptr()
+
+    def sub(self, coff, C):
+        return View(self.buf, self.coff + coff, C)
+
+    def torch(self):
+        return self.buf[..., self.coff:self.coff + self.C]
+
+
+class PackedConv:
+    """Device-resident packed weights of one nn.Conv2d / nn.ConvTranspose2d.
+
+    fp32 CUDA-core layout: [k*k taps][Cin][cout_pad] (cout fastest).  `in_perm` reorders the
+    input channels (used where our concat buffers are laid out differently from the
+    reference's torch.cat order).
+    """
+
+    def __init__(self, mod, device, in_perm=None):
+        w = mod.weight.detach().to(device=device, dtype=torch.float32)
+        self.transposed = isinstance(mod, torch.nn.ConvTranspose2d)
+        if self.transposed:
+            cin, cout, kh, kw = w.shape
+            taps = w.permute(2, 3, 0, 1)  # [kh, kw, cin, cout]
+        else:
+            cout, cin, kh, kw = w.shape
+            taps = w.permute(2, 3, 1, 0)
+        assert kh == kw
+        self.k = kh
+        self.stride = mod.stride[0]
+        self.pad = mod.padding[0]
+        self.Cin, self.Cout = cin, cout
+        taps = taps.reshape(kh * kw, cin, cout)
+        if in_perm is not None:
+            taps = taps[:, in_perm.to(device), :]
+        self.cout_pad = (cout + 15) // 16 * 16
+        packed = torch.zeros(kh * kw, cin, self.cout_pad, device=device, dtype=torch.float32)
+        packed[:, :, :cout] = taps
+        self.w32 = packed.contiguous()
+        self.bias = None if mod.bias is None else mod.bias.detach().to(device=device, dtype=torch.float32).contiguous()
+
+    def launches(self, H, W):
+        """-> (Ho, Wo, [dict(Hs, Ws, o_step, o_off_y, o_off_x, i_step, taps=[(dy, dx, wtap)])])"""
+        k, s, p = self.k, self.stride, self.pad
+        if not self.transposed:
+            Ho = (H + 2 * p - k) // s + 1
+            Wo = (W + 2 * p - k) // s + 1
+            taps = [(ky - p, kx - p, ky * k + kx) for ky in range(k) for kx in range(k)]
+            return Ho, Wo, [dict(Hs=Ho, Ws=Wo, o_step=1, o_off_y=0, o_off_x=0, i_step=s, taps=taps)]
+        if s == 1:  # ConvTranspose2d(k, 1, p): oy = iy - p + ky
+            taps = [(p - ky, p - kx, ky * k + kx) for ky in range(k) for kx in range(k)]
+            return H, W, [dict(Hs=H, Ws=W, o_step=1, o_off_y=0, o_off_x=0, i_step=1, taps=taps)]
+        assert s == 2 and k == 5 and p == 2, "only ConvTranspose2d(5, 2, 2, output_padding=1) strided"
+        out = []
+        for py in range(2):
+            for px in range(2):
+                taps = [((py + p - ky) // 2, (px + p - kx) // 2, ky * k + kx)
+                        for ky in range(k) if (py + p - ky) % 2 == 0
+                        for kx in range(k) if (px + p - kx) % 2 == 0]
+                out.append(dict(Hs=H, Ws=W, o_step=2, o_off_y=py, o_off_x=px, i_step=1, taps=taps))
+        return 2 * H, 2 * W, out
+
+
+class Program:
+    """Static launch list + the buffers it owns."""
+
+    def __init__(self, device):
+        self.device = device
+        self.ops = []       # callables taking the raw stream pointer
+        self.keep = []      # ctypes structs / tensors that must outlive the ops
+        self.pool = {}      # (shape, dtype) -> [free tensors]
+        self.bytes = 0
+        self.io = {}
+        self.graph = None
+        self.flops = 0      # dense conv flops of one run (MAC * 2)
+
+    def run(self, use_graph=False):
+        if use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+            return
+        sp = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        for op in self.ops:
+            op(sp)
+
+    def _capture(self):
+        # warm-up run on a side stream (lazy cudaFuncSetAttribute calls must not be captured)
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.run(False)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            sp = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            for op in self.ops:
+                op(sp)
+        self.graph = g
+
+
+class Builder:
+    def __init__(self, device, act_dtype):
+        self.device = device
+        self.act_dtype = act_dtype
+        self.prog = Program(device)
+
+    # ---- memory ----
+    def alloc(self, N, H, W, Cc, dtype=None, zero=False):
+        dtype = dtype or self.act_dtype
+        key = ((N, H, W, Cc), dtype)
+        free = self.prog.pool.setdefault(key, [])
+        if free and not zero:
+            t = free.pop()
+        else:
+            t = (torch.zeros if zero else torch.empty)((N, H, W, Cc), device=self.device, dtype=dtype)
+            self.prog.bytes += t.numel() * t.element_size()
+        return View(t)
+
+    def release(self, *views):
+        for v in views:
+            self.prog.pool.setdefault((tuple(v.buf.shape), v.buf.dtype), []).append(v.buf)
+
+    def raw(self, shape, dtype, zero=False):
+        t = (torch.zeros if zero else torch.empty)(shape, device=self.device, dtype=dtype)
+        self.prog.bytes += t.numel() * t.element_size()
+        self.prog.keep.append(t)
+        return t
+
+    # ---- ops ----
+    def op(self, name, *args):
+        fn = getattr(L.load(), name)
+
+        def run(sp, fn=fn, args=args, name=name):
+            rc = fn(*args, sp)
+            if rc:
+                L.check(rc, name)
+        self.prog.ops.append(run)
+
+    def torch_op(self, f):
+        self.prog.ops.append(lambda sp, f=f: f())
+
+    def conv(self, pc, x, out=None, act=L.ACT_NONE, epi=L.EPI_LINEAR, res=None, mul=None, in_scale=None,
+             y2=None, out_dtype=None):
+        assert x.C == pc.Cin, (x.C, pc.Cin)
+        Ho, Wo, launches = pc.launches(x.H, x.W)
+        if out is None:
+            out = self.alloc(x.N, Ho, Wo, pc.Cout, out_dtype)
+        assert (out.N, out.H, out.W, out.C) == (x.N, Ho, Wo, pc.Cout), ((out.N, out.H, out.W, out.C), (x.N, Ho, Wo, pc.Cout))
+        for ln in launches:
+            d = L.ConvDesc()
+            d.x, d.y, d.w = x.ptr(), out.ptr(), pc.w32.data_ptr()
+            d.y2 = y2.ptr() if y2 is not None else None
+            d.bias = pc.bias.data_ptr() if pc.bias is not None else None
+            d.in_scale = in_scale.data_ptr() if in_scale is not None else None
+            d.N, d.H, d.W = x.N, x.H, x.W
+            d.Cin, d.x_cstride, d.x_coff = x.C, x.cstride, x.coff
+            d.Ho, d.Wo = Ho, Wo
+            d.Cout, d.y_cstride, d.y_coff = pc.Cout, out.cstride, out.coff
+            if y2 is not None:
+                assert y2.dtype == out.dtype and (y2.N, y2.H, y2.W, y2.C) == (out.N, out.H, out.W, out.C)
+                d.y2_cstride, d.y2_coff = y2.cstride, y2.coff
+            for f in ("Hs", "Ws", "o_step", "o_off_y", "o_off_x", "i_step"):
+                setattr(d, f, ln[f])
+            d.ntaps = len(ln["taps"])
+            for i, (dy, dx, wt) in enumerate(ln["taps"]):
+                d.dy[i], d.dx[i], d.wtap[i] = dy, dx, wt
+            if res is not None:
+                assert res.dtype == x.dtype
+                d.res, d.res_cstride, d.res_coff = res.ptr(), res.cstride, res.coff
+                if epi == L.EPI_BILERP:
+                    d.res_H, d.res_W = res.H, res.W
+                else:
+                    assert (res.H, res.W, res.C) == (Ho, Wo, pc.Cout)
+            if mul is not None:
+                assert mul.dtype == x.dtype and (mul.H, mul.W, mul.C) == (Ho, Wo, pc.Cout)
+                d.mul, d.mul_cstride, d.mul_coff = mul.ptr(), mul.cstride, mul.coff
+            d.act, d.epi = act, epi
+            d.x_dtype, d.y_dtype = _DT[x.dtype], _DT[out.dtype]
+            d.cout_pad = pc.cout_pad
+            L.check(L.load().rgbd_conv_validate(C.byref(d)), "rgbd_conv_validate")
+            self.prog.keep.append(d)
+            self.op("rgbd_conv_simt", C.byref(d))
+            self.prog.flops += 2 * x.N * ln["Hs"] * ln["Ws"] * len(ln["taps"]) * pc.Cin * pc.Cout
+        self.prog.keep.extend([pc, x.buf, out.buf])
+        return out
+
+    def se_scale(self, x, w1, w2, plus_one):
+        """SE_Block channel gate of `x` -> fp32 [N, C] scale tensor."""
+        Cr = w1.shape[0]
+        HW = x.H * x.W
+        nchunk = max(1, min(64, HW // 64))
+        partial = self.raw((x.N, nchunk, x.C), torch.float32)
+        scale = self.raw((x.N, x.C), torch.float32)
+        self.op("rgbd_se_scale", x.ptr(), _DT[x.dtype], x.N, HW, x.C, x.cstride, x.coff, w1.data_ptr(),
+                w2.data_ptr(), Cr, int(plus_one), partial.data_ptr(), nchunk, scale.data_ptr())
+        self.prog.keep.extend([w1, w2])
+        return scale
+
+    def maxpool7s3(self, x):
+        assert x.coff == 0 and x.C == x.cstride
+        out = self.alloc(x.N, (x.H - 7) // 3 + 1, (x.W - 7) // 3 + 1, x.C, x.dtype)
+        self.op("rgbd_maxpool7s3", x.ptr(), out.ptr(), _DT[x.dtype], x.N, x.H, x.W, x.C)
+        return out
