@@ -98,6 +98,9 @@ typedef struct rgbd_conv_desc {
 /* fp32-accumulate CUDA-core path: weights fp32 [ntaps_total][Cin][cout_pad]. Used for the
  * fp32 parity mode and for the 3/1-channel image-side layers. */
 int rgbd_conv_simt(const rgbd_conv_desc *d, void *stream);
+/* argument check shared by both conv paths; sizeof(rgbd_conv_desc) for binding self-checks */
+int rgbd_conv_validate(const rgbd_conv_desc *d);
+int rgbd_conv_desc_size(void);
 
 /* tcgen05 tensor-core path (bf16 operands, fp32 TMEM accumulators, TMA-staged NHWC tiles).
  * Weights bf16 [ntaps_total][cout_pad][cin_pad] (K-major).  The plan object owns the TMA

@@ -19,3 +19,4 @@ extern "C" int rgbd_abi_version(void) { return 1; }
 extern "C" int64_t rgbd_launch_count(int reset) {
     return reset ? g_launches.exchange(0) : g_launches.load();
 }
+extern "C" int rgbd_conv_desc_size(void) { return (int)sizeof(rgbd_conv_desc); }

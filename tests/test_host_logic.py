@@ -1,0 +1,141 @@
+"""Host-side logic that needs no GPU: launch decomposition of the conv family (checked by a
+torch-CPU emulation of the kernel's documented semantics), context-buffer permutations,
+CDF tables, the exact-reciprocal identity the rANS encoder relies on, and error behaviour."""
+import json
+import random
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import rgbd_b200
+from rgbd_b200.engine import PackedConv
+
+
+def emulate(pc, x_nhwc):
+    """The kernel contract of include/rgbd_b200.h in slow torch: per launch, per tap."""
+    N, H, W, Cin = x_nhwc.shape
+    Ho, Wo, launches = pc.launches(H, W)
+    y = torch.zeros(N, Ho, Wo, pc.Cout)
+    for ln in launches:
+        oy = torch.arange(ln["Hs"])
+        ox = torch.arange(ln["Ws"])
+        acc = torch.zeros(N, ln["Hs"], ln["Ws"], pc.cout_pad)
+        for dy, dx, wt in ln["taps"]:
+            iy, ix = oy * ln["i_step"] + dy, ox * ln["i_step"] + dx
+            vy, vx = (iy >= 0) & (iy < H), (ix >= 0) & (ix < W)
+            g = x_nhwc[:, iy.clamp(0, H - 1)][:, :, ix.clamp(0, W - 1)]
+            g = g * (vy[:, None] & vx[None, :])[None, :, :, None]
+            acc += g @ pc.w32[wt]
+        acc = acc[..., :pc.Cout] + pc.bias
+        y[:, ln["o_off_y"]::ln["o_step"], ln["o_off_x"]::ln["o_step"]] = acc
+    return y
+
+
+@pytest.mark.parametrize("mod", [
+    nn.Conv2d(5, 7, 5, 2, 2), nn.Conv2d(4, 6, 3, 1, 1), nn.Conv2d(6, 3, 1), nn.Conv2d(4, 4, 3, 2, 0),
+    nn.Conv2d(3, 8, 5, 1, 2),
+    nn.ConvTranspose2d(5, 6, 5, 2, padding=2, output_padding=1),
+    nn.ConvTranspose2d(4, 3, 3, 1, padding=1, output_padding=0),
+])
+def test_launch_decomposition_equals_torch(mod):
+    torch.manual_seed(0)
+    x = torch.randn(2, mod.in_channels, 9, 12)
+    with torch.no_grad():
+        want = mod(x)
+        got = emulate(PackedConv(mod, "cpu"), x.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2)
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
+
+
+def test_deconv_phase_flops_equal_dense_count():
+    pc = PackedConv(nn.ConvTranspose2d(4, 4, 5, 2, padding=2, output_padding=1), "cpu")
+    _, _, launches = pc.launches(8, 8)
+    assert sorted(len(l["taps"]) for l in launches) == [4, 6, 6, 9]   # 25 taps in total
+
+
+def test_context_buffer_permutation():
+    """Our concat order [hyper, ch, loc_r, loc_d] with permuted weights == the reference's order."""
+    net = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4)
+    M = net.M
+    for idx in (0, 2):
+        g = net.slice_ch[idx]
+        o, perms = net._ctx_layout(idx)
+        parts = {"hyper_r": torch.randn(1, 2 * M, 2, 2), "hyper_d": torch.randn(1, 2 * M, 2, 2),
+                 "loc_r": torch.randn(1, 2 * g, 2, 2), "loc_d": torch.randn(1, 2 * g, 2, 2)}
+        base = ["hyper_r", "hyper_d"]
+        if idx:
+            parts["ch_r"], parts["ch_d"] = torch.randn(1, 2 * g, 2, 2), torch.randn(1, 2 * g, 2, 2)
+            base += ["ch_r", "ch_d"]
+        ours_all = torch.cat([parts[k] for k in base + ["loc_r", "loc_d"]], 1)
+        ref_orders = {"r_anchor": base, "d_anchor": ["loc_r"] + base, "r_nonanchor": ["loc_r", "loc_d"] + base,
+                      "d_nonanchor": ["loc_r", "loc_d"] + base}
+        mods = {"r_anchor": net.rgb_entropy_parameters_anchor, "d_anchor": net.depth_entropy_parameters_anchor,
+                "r_nonanchor": net.rgb_entropy_parameters_nonanchor, "d_nonanchor": net.depth_entropy_parameters_nonanchor}
+        for name, order in ref_orders.items():
+            ref_x = torch.cat([parts[k] for k in order], 1)
+            perm = perms[name]
+            width = ref_x.shape[1]
+            assert mods[name][idx].fusion[0].in_channels == width
+            ours = ours_all[:, :width]
+            assert torch.equal(ours, ref_x[:, perm])
+            conv = mods[name][idx].fusion[0]
+            with torch.no_grad():
+                want = conv(ref_x)
+                got = F.conv2d(ours, conv.weight[:, perm], conv.bias)
+            assert torch.allclose(got, want, atol=1e-4)
+
+
+def test_gaussian_tables_equal_reference(golden_dir, built_lib):
+    g = np.load(f"{golden_dir}/gauss_tables.npz")
+    net = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4)
+    assert net.update(force=True)
+    gc = net.depth_gaussian_conditional
+    assert np.array_equal(gc.quantized_cdf.numpy(), g["cdf"])
+    assert np.array_equal(gc.cdf_length.numpy(), g["lengths"])
+    assert np.array_equal(gc.offset.numpy(), g["offsets"])
+    assert np.array_equal(gc.scale_table.numpy(), g["scale_table"])
+    assert int(g["lengths"].sum()) == 27256
+
+
+def test_load_state_dict_resizes_tables():
+    a = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4)
+    a.update(force=True)
+    b = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4)
+    b.load_state_dict(a.state_dict())          # checkpoint saved after update() into a fresh model
+    assert torch.equal(b.rgb_gaussian_conditional.quantized_cdf, a.rgb_gaussian_conditional.quantized_cdf)
+    b.load_state_dict(a.state_dict())          # and into an already-updated one
+    with pytest.raises(RuntimeError):
+        bad = dict(a.state_dict())
+        bad.pop("g_a.rgb_analysis_transform.0.weight")
+        b.load_state_dict(bad)
+
+
+def test_exact_reciprocal_division():
+    """q = mulhi(x, rcp) >> shift == x // f for every x < 2^63 the encoder can see
+    (ryg_rans rans64.h:167-247; csrc/rans.cu make_reciprocal)."""
+    rnd = random.Random(5)
+    for f in list(range(2, 70)) + [rnd.randrange(2, 65536) for _ in range(400)] + [65535, 32768, 32769]:
+        s = (f - 1).bit_length()
+        rcp = ((1 << (s + 63)) + f - 1) // f
+        assert rcp < (1 << 64)
+        for x in [1 << 31, (1 << 31) + 1, (f << 47) - 1, f << 31] + [rnd.randrange(1 << 31, f << 47) for _ in range(60)]:
+            assert ((x * rcp) >> 64) >> (s - 1) == x // f, (f, x)
+
+
+def test_cpu_device_is_refused_without_fallback(built_lib):
+    net = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4).eval()
+    net.update(force=True)
+    with pytest.raises(rgbd_b200.lib.RgbdError, match="no CPU fallback"):
+        net.compress(torch.zeros(1, 3, 128, 128), torch.zeros(1, 1, 128, 128))
+    with pytest.raises(ValueError, match="multiples of 64"):
+        net.compress(torch.zeros(1, 3, 100, 128), torch.zeros(1, 1, 100, 128))
+
+
+def test_model_zoo_lookup_order():
+    # substring lookup in dict order must find R2D before the bidirectional model
+    name = "ELIC_united_R2D_q2"
+    hit = next(v for k, v in rgbd_b200.modelZoo.items() if name.find(k) != -1)
+    assert hit is rgbd_b200.ELIC_united_R2D
