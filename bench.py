@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Throughput bench of the ELIC_united compress+decompress hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the CPU implementation of the path
+
+A step = compress + decompress of one batch of synthetic NYUv2-shaped pairs (480x640 padded to
+512x640, calibrated random-init weights: rgbd_b200.synthetic).  `value` has the inputs resident
+in HBM; `e2e` goes through the public API with pinned HOST buffers (H2D of the images and D2H of
+the reconstruction inside the timed region).  The rANS strings are host `bytes` in both, because
+that is the codec's API contract (they are the compressed file).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "RGB-D pairs/sec compress+decompress 480x640"
+UNIT = "pairs/s"
+GFLOP_PER_PAIR = 721.2 + 785.1   # dense conv count, SURVEY §8(d)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="pairs per GPU per step (default: by precision)")
+    ap.add_argument("--precision", default=os.environ.get("RGBD_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--preset", default="realistic")
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--cpu-pairs", type=int, default=2, help="pairs in the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+def make_inputs(n, H, W, seed):
+    from rgbd_b200.synthetic import pad_to_multiple, synthetic_pairs
+    rgb, depth = synthetic_pairs(n, H, W, seed=seed)
+    return pad_to_multiple(rgb), pad_to_multiple(depth)
+
+
+def cpu_arm(args, pairs, steps, warmup):
+    """The path's CPU implementation timed on this box's host cores: oracle/model_oracle.py (torch
+    CPU fp32 restatement, pinned bit-exactly to the reference) + the reference's own compiled rANS
+    coder from oracle/_ref when it was built (else the C restatement).  Batch 1 loop like
+    testing/tester_united.py, no file I/O."""
+    import torch
+    import rgbd_b200
+    from oracle.model_oracle import OracleCodec
+    from oracle.ref_loader import ref_ext_available
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    net = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4).eval()
+    net.load_state_dict(rgbd_b200.synthetic.synthetic_state_dict(net, 0, args.preset))
+    net.update(force=True)
+    use_ref = ref_ext_available()
+    orc = OracleCodec(net.state_dict(), use_ref_coder=use_ref)
+    rgb, depth = make_inputs(pairs, args.height, args.width, seed=1234)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for i in range(pairs):
+            c = orc.compress(rgb[i:i + 1], depth[i:i + 1])
+            orc.decompress(c["r_strings"], c["d_strings"], c["shape"])
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": pairs * len(times) / total, "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "port", "coder": "reference ans (oracle/_ref)" if use_ref else "C restatement",
+            "sample": f"{pairs} pair(s) x {len(times)} timed pass(es) of {args.height}x{args.width} "
+                      f"compress+decompress, batch 1, torch CPU fp32 ({warmup} warm-up)",
+            "ms_per_pair": 1e3 * total / (pairs * len(times))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    cb = cpu_arm(args, 1, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_pair"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"ELIC_united compress+decompress, {args.height}x{args.width} -> 512x640 "
+                                   f"pairs, batch 1 per step, preset {args.preset}", "host": "cpu"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "coder")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    entry.build()
+    import rgbd_b200
+    from rgbd_b200 import lib as L
+    from rgbd_b200.parallel import add_pair_stats, allreduce_stats, new_stats, summarize
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch or (4 if args.precision == "fp32" else 16)
+
+    net = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4, precision=args.precision).eval()
+    net.load_state_dict(rgbd_b200.synthetic.synthetic_state_dict(net, 0, args.preset))
+    net.update(force=True)
+    net = net.to(dev)
+    # each rank owns its contiguous shard of the global batch (weak scaling: B pairs per GPU)
+    rgb_h, depth_h = make_inputs(B, args.height, args.width, seed=1234 + rank * B)
+    rgb_h, depth_h = rgb_h.pin_memory(), depth_h.pin_memory()
+    rgb_d, depth_d = rgb_h.to(dev), depth_h.to(dev)
+    Hp, Wp = rgb_h.shape[-2:]
+
+    def step_device():
+        c = net.compress(rgb_d, depth_d)
+        r = net.decompress(c["r_strings"], c["d_strings"], c["shape"])
+        return c, r
+
+    def step_e2e():
+        x, d = rgb_h.to(dev, non_blocking=True), depth_h.to(dev, non_blocking=True)
+        c = net.compress(x, d)
+        r = net.decompress(c["r_strings"], c["d_strings"], c["shape"])
+        return c, r["x_hat"]["r"].cpu(), r["x_hat"]["d"].cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    W_, K = max(3, args.warmup), max(1, args.steps)
+    for _ in range(W_):
+        step_device()
+    # L2 note: one step streams > 1 GB of activations per image through HBM, far beyond the 126 MB L2,
+    # so consecutive steps cannot serve each other from cache (no explicit flush needed).
+    L.load().rgbd_launch_count(1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, (c, r) = timed(step_device, K)
+    launches = int(L.load().rgbd_launch_count(1))
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * K / (ms / 1e3)
+
+    step_e2e()
+    ms_e2e, (c2, xr, xd) = timed(step_e2e, K)
+    e2e_value = world * B * K / (ms_e2e / 1e3)
+    stream_bytes = sum(len(s) for key in ("r_strings", "d_strings") for grp in c2[key] for s in grp)
+    h2d = rgb_h.numel() * 4 + depth_h.numel() * 4 + stream_bytes
+    d2h = stream_bytes + xr.numel() * 4 + xd.numel() * 4
+
+    # roofline of the dominant kernel family (the implicit-GEMM conv): per-launch CUDA events on the
+    # launching stream, over the same workload
+    roof = conv_roofline(net, B, Hp, Wp, dev)
+    stats = add_pair_stats(new_stats(), c["r_strings"], c["d_strings"], rgb_d[:, :, :args.height, :args.width],
+                           depth_d[:, :, :args.height, :args.width],
+                           r["x_hat"]["r"][:, :, :args.height, :args.width], r["x_hat"]["d"][:, :, :args.height, :args.width])
+    stats = summarize(allreduce_stats(stats, dev))
+    if rank == 0:
+        pk, pk_src = peaks()
+        tens_peak = pk["bf16_tflops_sustained"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": f"ELIC_united compress+decompress, {world}x{B} pairs/step of "
+                                   f"{args.height}x{args.width} (padded {Hp}x{Wp}), preset {args.preset}, "
+                                   f"weights calibrated random-init", "pairs_per_gpu": B, "precision": args.precision,
+                       "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
+                       "parallelism": f"dp{world} (images sharded, no data-path collective)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": roof["tflops"], "peak": tens_peak, "unit": "TFLOP/s",
+                         "frac": roof["tflops"] / tens_peak, "traffic": None,
+                         "kernel": roof["kernel"], "launches": roof["launches"], "peak_source": pk_src + " bf16 sustained",
+                         "share_of_step": roof["ms"] / (ms / K), "algorithmic_gflop_per_pair": GFLOP_PER_PAIR,
+                         "whole_step_tflops": GFLOP_PER_PAIR * B * K / ms},
+            "quality": stats,
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = {k: v for k, v in cpu_arm(args, args.cpu_pairs, 1, 0).items()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def conv_roofline(net, B, Hp, Wp, dev):
+    """Algorithmic conv flops / sum of conv launch durations for one encoder + decoder pass."""
+    import ctypes as C
+    import torch
+    total_ms, total_flops, n = 0.0, 0.0, 0
+    with torch.cuda.device(dev):
+        for prog in (net._program("encoder", B, Hp, Wp), net._program("decoder", B, Hp // 64, Wp // 64)):
+            sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            evs = []
+            for op in prog.ops:
+                if getattr(op, "is_conv", False):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    op(sp)
+                    b.record()
+                    evs.append((a, b))
+                else:
+                    op(sp)
+            torch.cuda.synchronize(dev)
+            total_ms += sum(a.elapsed_time(b) for a, b in evs)
+            total_flops += prog.flops
+            n += len(evs)
+    return {"tflops": total_flops / (total_ms / 1e3) / 1e12, "ms": total_ms, "launches": n,
+            "kernel": "conv_simt_kernel" if net.precision == "fp32" else "conv (tc + simt)"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -17,13 +17,24 @@ NVCC_FLAGS = [
 ]
 
 
-def _stale():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+def _source_hash():
+    """Content hash of everything the library is built from (mtimes do not survive the snapshot
+    copy to the GPU box, contents do)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [
         os.path.join(HERE, "..", "include", "rgbd_b200.h"), os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read())
+    return h.hexdigest()
+
+
+def _stale():
+    stamp = LIB + ".srchash"
+    if not os.path.exists(LIB) or not os.path.exists(stamp):
+        return True
+    return open(stamp).read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
@@ -51,6 +62,8 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
+    with open(LIB + ".srchash", "w") as fh:
+        fh.write(_source_hash())
     return LIB
 
 

@@ -309,7 +309,7 @@ class ELIC_united(nn.Module):
         s = b.se_scale(x, w1, w2, plus_one=False)
         return b.conv(self._pc(m.deconv), x, out=out, y2=y2, in_scale=s, act=NONE if m.is_last else LEAKY)
 
-    def _h_s(self, b, zcat, ctx_r, ctx_d):
+    def _h_s(self, b, zcat, ctx_r, ctx_d, ctx_r2=None):
         """HyperSynthesisEXcross / EXSingle (synthesis.py:305-343).  zcat = [z_r | z_d | z_r] so both
         cat orders are views; the last stage writes straight into the context buffers."""
         Nz, M = self.N, self.M
@@ -330,7 +330,7 @@ class ELIC_united(nn.Module):
             self._hyper_block(b, hs.d_h_s1, zcat.sub(Nz, 2 * Nz), out=c1.sub(M, M))
             self._hyper_block(b, hs.r_h_s2, c1.sub(0, M), out=c2.sub(0, M2), y2=c2.sub(2 * M2, M2))
             self._hyper_block(b, hs.d_h_s2, c1.sub(M, 2 * M), out=c2.sub(M2, M2))
-            self._hyper_block(b, hs.r_h_s3, c2.sub(0, M2), out=ctx_r)
+            self._hyper_block(b, hs.r_h_s3, c2.sub(0, M2), out=ctx_r, y2=ctx_r2)
             self._hyper_block(b, hs.d_h_s3, c2.sub(M2, 2 * M2), out=ctx_d)
         b.release(c1, c2)
 
@@ -342,7 +342,9 @@ class ELIC_united(nn.Module):
     def _ctx_layout(self, idx):
         """Channel layout of the shared context buffer for slice idx.
         ours:  [hyper_r 2M | hyper_d 2M | ch_r 2g | ch_d 2g | loc_r 2g | loc_d 2g]   (ch_* only idx>0)
-        Returns offsets and, per EntropyParametersEX, (width, perm) where perm[j] = index into the
+        R2D additionally keeps an rgb-only buffer [hyper_r 2M | ch_r 2g | loc_r 2g] because its rgb
+        branch must not see depth (elic_united_R2D.py:82-90).
+        Returns (offsets, perms, rgb_offsets): per EntropyParametersEX perm[j] = index into the
         reference's torch.cat order (elic_united.py:288,302,317,333) of our channel j."""
         M, g = self.M, self.slice_ch[idx]
         has_ch = idx > 0
@@ -368,12 +370,19 @@ class ELIC_united(nn.Module):
         base = [("hyper_r", 2 * M), ("hyper_d", 2 * M)] + ([("ch_r", 2 * g), ("ch_d", 2 * g)] if has_ch else [])
         lr, ld = ("loc_r", 2 * g), ("loc_d", 2 * g)
         plans = {
-            "r_anchor": perm(base, base),
             "d_anchor": perm([lr] + base, base + [lr]),
-            "r_nonanchor": perm([lr, ld] + base, base + [lr, ld]),
             "d_nonanchor": perm([lr, ld] + base, base + [lr, ld]),
         }
-        return o, plans
+        o_r = None
+        if self.cross:
+            plans["r_anchor"] = perm(base, base)
+            plans["r_nonanchor"] = perm([lr, ld] + base, base + [lr, ld])
+        else:
+            rbase = [("hyper_r", 2 * M)] + ([("ch_r", 2 * g)] if has_ch else [])
+            plans["r_anchor"] = perm(rbase, rbase)
+            plans["r_nonanchor"] = perm([lr] + rbase, rbase + [lr])
+            o_r = {"hyper_r": 0, "ch_r": 2 * M, "loc_r": 2 * M + (2 * g if has_ch else 0)}
+        return o, plans, o_r
 
     def _ep(self, b, m, x, perm, out):
         """EntropyParametersEX (entropy.py:56-78): fusion(x + se(x)) -> fp32 (scales | means)"""
@@ -386,36 +395,45 @@ class ELIC_united(nn.Module):
         b.release(t2)
         return y
 
-    def _channel_ctx(self, b, m, x, out):
+    def _channel_ctx(self, b, m, x, out, y2=None):
         t1 = b.conv(self._pc(m.fushion[0]), x, act=RELU)
         t2 = b.conv(self._pc(m.fushion[2]), t1, act=RELU)
         b.release(t1)
-        b.conv(self._pc(m.fushion[4]), t2, out=out)
+        b.conv(self._pc(m.fushion[4]), t2, out=out, y2=y2)
         b.release(t2)
 
-    def _context_chain(self, b, ctx, yhat_r, yhat_d, code_step):
-        """The 20-stage serial chain (elic_united.py:265-348 / 454-541).  code_step(mod, idx, parity,
-        params_view, g, coff) emits the kernels that turn Gaussian params into y_hat at the parity
-        sites (quantise in the encoder, rANS-decode in the decoder, ste+likelihood in forward)."""
-        assert self.cross, "R2D context chain is built by the subclass"
+    def _context_chain(self, b, ctx, ctx_rgb, yhat_r, yhat_d, code_step):
+        """The 20-stage serial chain (elic_united.py:265-348 / 454-541; R2D: elic_united_R2D.py:73-326).
+        code_step(which, idx, parity, params_view, g, coff) emits the kernels that turn Gaussian
+        params into y_hat at the parity sites (quantise in the encoder, rANS-decode in the decoder,
+        ste + likelihood in forward).  ctx_rgb is the rgb-only context buffer of the R2D variant."""
+        cross = self.cross
         for idx, g in enumerate(self.slice_ch):
             coff = sum(self.slice_ch[:idx])
-            o, perms = self._ctx_layout(idx)
+            o, perms, o_r = self._ctx_layout(idx)
             params = b.alloc(ctx.N, ctx.H, ctx.W, 2 * g, torch.float32)
+
+            def rgb_copy(name):
+                return None if cross else ctx_rgb.sub(o_r[name], 2 * g)
+
             if idx > 0:
-                self._channel_ctx(b, self.rgb_channel_context[idx], yhat_r.sub(0, coff), ctx.sub(o["ch_r"], 2 * g))
+                self._channel_ctx(b, self.rgb_channel_context[idx], yhat_r.sub(0, coff), ctx.sub(o["ch_r"], 2 * g),
+                                  y2=rgb_copy("ch_r"))
                 self._channel_ctx(b, self.depth_channel_context[idx], yhat_d.sub(0, coff), ctx.sub(o["ch_d"], 2 * g))
             pre = o["loc_r"]
             # (1) rgb anchor
-            self._ep(b, self.rgb_entropy_parameters_anchor[idx], ctx.sub(0, pre), perms["r_anchor"], params)
+            x = ctx.sub(0, pre) if cross else ctx_rgb.sub(0, o_r["loc_r"])
+            self._ep(b, self.rgb_entropy_parameters_anchor[idx], x, perms["r_anchor"], params)
             code_step("r", idx, 0, params, g, coff)
-            b.conv(self._pc(self.rgb_local_context[idx]), yhat_r.sub(coff, g), out=ctx.sub(o["loc_r"], 2 * g))
+            b.conv(self._pc(self.rgb_local_context[idx]), yhat_r.sub(coff, g), out=ctx.sub(o["loc_r"], 2 * g),
+                   y2=rgb_copy("loc_r"))
             # (2) depth anchor
             self._ep(b, self.depth_entropy_parameters_anchor[idx], ctx.sub(0, pre + 2 * g), perms["d_anchor"], params)
             code_step("d", idx, 0, params, g, coff)
             b.conv(self._pc(self.depth_local_context[idx]), yhat_d.sub(coff, g), out=ctx.sub(o["loc_d"], 2 * g))
             # (3) rgb non-anchor
-            self._ep(b, self.rgb_entropy_parameters_nonanchor[idx], ctx.sub(0, pre + 4 * g), perms["r_nonanchor"], params)
+            x = ctx.sub(0, pre + 4 * g) if cross else ctx_rgb.sub(0, o_r["loc_r"] + 2 * g)
+            self._ep(b, self.rgb_entropy_parameters_nonanchor[idx], x, perms["r_nonanchor"], params)
             code_step("r", idx, 1, params, g, coff)
             b.conv(self._pc(self.rgb_local_context_anchor_with_nonanchor[idx]), yhat_r.sub(coff, g),
                    out=ctx.sub(o["loc_r"], 2 * g))
@@ -423,6 +441,12 @@ class ELIC_united(nn.Module):
             self._ep(b, self.depth_entropy_parameters_nonanchor[idx], ctx.sub(0, pre + 4 * g), perms["d_nonanchor"], params)
             code_step("d", idx, 1, params, g, coff)
             b.release(params)
+
+    def _ctx_buffers(self, b, B, h, w):
+        M, gm = self.M, max(self.slice_ch)
+        ctx = b.alloc(B, h, w, 4 * M + 8 * gm)
+        ctx_rgb = None if self.cross else b.alloc(B, h, w, 2 * M + 4 * gm)
+        return ctx, ctx_rgb
 
     # ------------------------------------------------------------------ programs
     def _gc(self, which):
@@ -492,8 +516,8 @@ class ELIC_united(nn.Module):
                  s["zout"].data_ptr(), s["zcap"], s["znw"].data_ptr())
             p.keep.append(t)
         self._dup(b, zcat.sub(0, Nz), zcat.sub(2 * Nz, Nz))
-        ctx = b.alloc(B, h, w, 4 * M + 8 * max(self.slice_ch))
-        self._h_s(b, zcat, ctx.sub(0, 2 * M), ctx.sub(2 * M, 2 * M))
+        ctx, ctx_rgb = self._ctx_buffers(b, B, h, w)
+        self._h_s(b, zcat, ctx.sub(0, 2 * M), ctx.sub(2 * M, 2 * M), None if ctx_rgb is None else ctx_rgb.sub(0, 2 * M))
         yhat = {"r": b.alloc(B, h, w, M, zero=True), "d": b.alloc(B, h, w, M, zero=True)}
         for which in ("r", "d"):
             t = yhat[which].buf
@@ -508,7 +532,7 @@ class ELIC_united(nn.Module):
                  s["ysym"].data_ptr(), s["yidx"].data_ptr(), ny, offs[(idx, parity)],
                  yhat[which].ptr(), _DT[yhat[which].dtype], yhat[which].cstride, coff)
 
-        self._context_chain(b, ctx, yhat["r"], yhat["d"], code_step)
+        self._context_chain(b, ctx, ctx_rgb, yhat["r"], yhat["d"], code_step)
         for which in ("r", "d"):
             s = st[which]
             t = self._tables("gc", which)
@@ -554,8 +578,8 @@ class ELIC_united(nn.Module):
             b.op("rgbd_eb_dequantize", s["zsym"].data_ptr(), B, hz * wz, Nz, med.data_ptr(), zh.ptr(),
                  _DT[zh.dtype], zh.cstride, zh.coff)
         self._dup(b, zcat.sub(0, Nz), zcat.sub(2 * Nz, Nz))
-        ctx = b.alloc(B, h, w, 4 * M + 8 * max(self.slice_ch))
-        self._h_s(b, zcat, ctx.sub(0, 2 * M), ctx.sub(2 * M, 2 * M))
+        ctx, ctx_rgb = self._ctx_buffers(b, B, h, w)
+        self._h_s(b, zcat, ctx.sub(0, 2 * M), ctx.sub(2 * M, 2 * M), None if ctx_rgb is None else ctx_rgb.sub(0, 2 * M))
         yhat = {"r": b.alloc(B, h, w, M, zero=True), "d": b.alloc(B, h, w, M, zero=True)}
         for which in ("r", "d"):
             t = yhat[which].buf
@@ -577,7 +601,7 @@ class ELIC_united(nn.Module):
                  yhat[which].ptr(), _DT[yhat[which].dtype], yhat[which].cstride, coff)
             p.keep.append(t)
 
-        self._context_chain(b, ctx, yhat["r"], yhat["d"], code_step)
+        self._context_chain(b, ctx, ctx_rgb, yhat["r"], yhat["d"], code_step)
         x_r, x_d = self._transform(b, self.g_s.rgb_synthesis_transform, self.g_s.depth_synthesis_transform,
                                    yhat["r"], yhat["d"])
         out_r = b.raw((B, 3, H, W), torch.float32)
@@ -609,8 +633,8 @@ class ELIC_united(nn.Module):
             b.op("rgbd_eb_likelihood", zs[which].ptr(), zs[which].cstride, B, hz * wz, Nz, ebp.data_ptr(),
                  eb.likelihood_bound, zh.ptr(), _DT[zh.dtype], zh.cstride, zh.coff, lz.data_ptr())
         self._dup(b, zcat.sub(0, Nz), zcat.sub(2 * Nz, Nz))
-        ctx = b.alloc(B, h, w, 4 * M + 8 * max(self.slice_ch))
-        self._h_s(b, zcat, ctx.sub(0, 2 * M), ctx.sub(2 * M, 2 * M))
+        ctx, ctx_rgb = self._ctx_buffers(b, B, h, w)
+        self._h_s(b, zcat, ctx.sub(0, 2 * M), ctx.sub(2 * M, 2 * M), None if ctx_rgb is None else ctx_rgb.sub(0, 2 * M))
         yhat = {"r": b.alloc(B, h, w, M, zero=True), "d": b.alloc(B, h, w, M, zero=True)}
         for which in ("r", "d"):
             t = yhat[which].buf
@@ -623,7 +647,7 @@ class ELIC_united(nn.Module):
                  params.ptr(), bound[which], gc.likelihood_bound, B, h, w, g, parity, yhat[which].ptr(),
                  _DT[yhat[which].dtype], yhat[which].cstride, coff, lik[which][0].data_ptr(), M, coff)
 
-        self._context_chain(b, ctx, yhat["r"], yhat["d"], code_step)
+        self._context_chain(b, ctx, ctx_rgb, yhat["r"], yhat["d"], code_step)
         x_r, x_d = self._transform(b, self.g_s.rgb_synthesis_transform, self.g_s.depth_synthesis_transform,
                                    yhat["r"], yhat["d"])
         out_r = b.raw((B, 3, H, W), torch.float32)

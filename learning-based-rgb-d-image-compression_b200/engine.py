@@ -169,6 +169,7 @@ class Builder:
             if rc:
                 L.check(rc, name)
         self.prog.ops.append(run)
+        return run
 
     def torch_op(self, f):
         self.prog.ops.append(lambda sp, f=f: f())
@@ -213,8 +214,10 @@ class Builder:
             d.cout_pad = pc.cout_pad
             L.check(L.load().rgbd_conv_validate(C.byref(d)), "rgbd_conv_validate")
             self.prog.keep.append(d)
-            self.op("rgbd_conv_simt", C.byref(d))
-            self.prog.flops += 2 * x.N * ln["Hs"] * ln["Ws"] * len(ln["taps"]) * pc.Cin * pc.Cout
+            run = self.op("rgbd_conv_simt", C.byref(d))
+            run.is_conv = True
+            run.flops = 2 * x.N * ln["Hs"] * ln["Ws"] * len(ln["taps"]) * pc.Cin * pc.Cout
+            self.prog.flops += run.flops
         self.prog.keep.extend([pc, x.buf, out.buf])
         return out
 

@@ -62,7 +62,7 @@ def test_context_buffer_permutation():
     M = net.M
     for idx in (0, 2):
         g = net.slice_ch[idx]
-        o, perms = net._ctx_layout(idx)
+        o, perms, _ = net._ctx_layout(idx)
         parts = {"hyper_r": torch.randn(1, 2 * M, 2, 2), "hyper_d": torch.randn(1, 2 * M, 2, 2),
                  "loc_r": torch.randn(1, 2 * g, 2, 2), "loc_d": torch.randn(1, 2 * g, 2, 2)}
         base = ["hyper_r", "hyper_d"]
