@@ -120,6 +120,11 @@ void rgbd_conv_tc_plan_destroy(rgbd_conv_tc_plan *p);
 int rgbd_se_scale(const void *x, int32_t dtype, int32_t N, int32_t HW, int32_t C, int32_t cstride,
                   int32_t coff, const float *w1, const float *w2, int32_t Cr, int32_t plus_one,
                   float *partial, int32_t nchunk, float *scale, void *stream);
+/* y = x * scale[n, c]: applies the SE gate as a separate pass for the tensor-core conv path,
+ * whose A operand goes HBM -> smem by TMA without passing through registers. */
+int rgbd_scale_channels(const void *x, void *y, int32_t dtype, const float *scale, int32_t N, int64_t HW,
+                        int32_t C, int32_t x_cstride, int32_t x_coff, int32_t y_cstride, int32_t y_coff,
+                        void *stream);
 /* F.max_pool2d(kernel 7, stride 3) of ESA (attention.py:88) */
 int rgbd_maxpool7s3(const void *x, void *y, int32_t dtype, int32_t N, int32_t H, int32_t W,
                     int32_t C, void *stream);

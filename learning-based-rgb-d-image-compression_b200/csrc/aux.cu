@@ -115,7 +115,38 @@ __global__ void copy_view_kernel(const T *__restrict__ x, T *__restrict__ y, int
     }
 }
 
+template <typename T>
+__global__ void scale_channels_kernel(const T *__restrict__ x, T *__restrict__ y, const float *__restrict__ scale,
+                                      int64_t pix_per_img, int64_t npix, int C, int xs, int xo, int ys, int yo) {
+    const int64_t total = npix * C;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = e / C;
+        const int c = (int)(e % C);
+        const int n = (int)(p / pix_per_img);
+        ElemIO<T>::st(y + p * ys + yo + c, ElemIO<T>::ld(x + p * xs + xo + c) * scale[(int64_t)n * C + c]);
+    }
+}
+
 }  // namespace
+
+extern "C" int rgbd_scale_channels(const void *x, void *y, int32_t dtype, const float *scale, int32_t N, int64_t HW,
+                                   int32_t C, int32_t x_cstride, int32_t x_coff, int32_t y_cstride, int32_t y_coff,
+                                   void *stream) {
+    RGBD_CHECK_ARG(x && y && scale, "null pointer");
+    RGBD_CHECK_ARG(N > 0 && HW > 0 && C > 0, "dims");
+    const int grid = rgbd_grid_for((int64_t)N * HW * C, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == RGBD_DT_F32)
+        scale_channels_kernel<float><<<grid, 256, 0, st>>>((const float *)x, (float *)y, scale, HW, (int64_t)N * HW, C,
+                                                           x_cstride, x_coff, y_cstride, y_coff);
+    else
+        scale_channels_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, scale,
+                                                                    HW, (int64_t)N * HW, C, x_cstride, x_coff,
+                                                                    y_cstride, y_coff);
+    RGBD_LAUNCH_CHECK();
+    return RGBD_OK;
+}
 
 extern "C" int rgbd_copy_view(const void *x, void *y, int32_t dtype, int64_t npix, int32_t C, int32_t x_cstride,
                               int32_t x_coff, int32_t y_cstride, int32_t y_coff, void *stream) {

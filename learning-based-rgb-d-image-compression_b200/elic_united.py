@@ -88,6 +88,7 @@ class ELIC_united(nn.Module):
 
         self.precision = kwargs.get("precision", "fp32")   # "fp32" | "bf16"
         self.use_cuda_graph = kwargs.get("cuda_graph", False)
+        self.tensor_cores = kwargs.get("tensor_cores", True)   # bf16 mode: tcgen05 convs (False: CUDA cores)
         self._packed = None      # id(module) -> PackedConv, rebuilt when weights change
         self._programs = {}
         self._aux = {}
@@ -484,7 +485,7 @@ class ELIC_united(nn.Module):
         return m.device_tables(self.device)
 
     def _build_encoder(self, B, H, W):
-        b = Builder(self.device, self.act_dtype)
+        b = Builder(self.device, self.act_dtype, self.tensor_cores and self.precision == "bf16")
         p = b.prog
         y_r, y_d, z_r, z_d = self._common_front(b, B, H, W)
         h, w = y_r.H, y_r.W
@@ -543,7 +544,7 @@ class ELIC_united(nn.Module):
         return p
 
     def _build_decoder(self, B, hz, wz):
-        b = Builder(self.device, self.act_dtype)
+        b = Builder(self.device, self.act_dtype, self.tensor_cores and self.precision == "bf16")
         p = b.prog
         Nz, M = self.N, self.M
         h, w = hz * 4, wz * 4
@@ -612,7 +613,7 @@ class ELIC_united(nn.Module):
         return p
 
     def _build_forward(self, B, H, W):
-        b = Builder(self.device, self.act_dtype)
+        b = Builder(self.device, self.act_dtype, self.tensor_cores and self.precision == "bf16")
         p = b.prog
         y_r, y_d, z_r, z_d = self._common_front(b, B, H, W)
         h, w = y_r.H, y_r.W
@@ -658,7 +659,7 @@ class ELIC_united(nn.Module):
         return p
 
     def _program(self, kind, *dims):
-        key = (kind, self.precision) + tuple(dims)
+        key = (kind, self.precision, self.tensor_cores) + tuple(dims)
         if key not in self._programs:
             self._require_cuda()
             with torch.cuda.device(self.device), torch.no_grad():

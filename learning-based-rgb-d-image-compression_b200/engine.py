@@ -71,6 +71,18 @@ class PackedConv:
         packed[:, :, :cout] = taps
         self.w32 = packed.contiguous()
         self.bias = None if mod.bias is None else mod.bias.detach().to(device=device, dtype=torch.float32).contiguous()
+        self._wtc = None
+
+    @property
+    def wtc(self):
+        """bf16 [taps][cout_pad][cin_pad] (K-major) for the tcgen05 path; cin_pad = multiple of 64."""
+        if self._wtc is None:
+            T, cin, cp = self.w32.shape
+            self.cin_pad = (cin + 63) // 64 * 64
+            w = torch.zeros(T, cp, self.cin_pad, device=self.w32.device, dtype=torch.bfloat16)
+            w[:, :, :cin] = self.w32.permute(0, 2, 1).to(torch.bfloat16)
+            self._wtc = w.contiguous()
+        return self._wtc
 
     def launches(self, H, W):
         """-> (Ho, Wo, [dict(Hs, Ws, o_step, o_off_y, o_off_x, i_step, taps=[(dy, dx, wtap)])])"""
@@ -106,6 +118,17 @@ class Program:
         self.io = {}
         self.graph = None
         self.flops = 0      # dense conv flops of one run (MAC * 2)
+        self.tc_plans = []  # rgbd_conv_tc_plan handles owned by this program
+        self.n_tc = 0
+        self.n_simt = 0
+
+    def __del__(self):
+        try:
+            lib = L.load()
+            for h in self.tc_plans:
+                lib.rgbd_conv_tc_plan_destroy(h)
+        except Exception:
+            pass
 
     def run(self, use_graph=False):
         if use_graph:
@@ -133,22 +156,26 @@ class Program:
 
 
 class Builder:
-    def __init__(self, device, act_dtype):
+    def __init__(self, device, act_dtype, tensor_cores=None):
         self.device = device
         self.act_dtype = act_dtype
         self.prog = Program(device)
+        # tcgen05 path: bf16 activations only
+        self.tensor_cores = (act_dtype == torch.bfloat16) if tensor_cores is None else tensor_cores
 
     # ---- memory ----
     def alloc(self, N, H, W, Cc, dtype=None, zero=False):
         dtype = dtype or self.act_dtype
-        key = ((N, H, W, Cc), dtype)
+        # 16-byte aligned pixel rows (TMA global strides, vector epilogue stores)
+        Cp = (Cc + 7) // 8 * 8 if dtype == torch.bfloat16 else Cc
+        key = ((N, H, W, Cp), dtype)
         free = self.prog.pool.setdefault(key, [])
         if free and not zero:
             t = free.pop()
         else:
-            t = (torch.zeros if zero else torch.empty)((N, H, W, Cc), device=self.device, dtype=dtype)
+            t = (torch.zeros if zero else torch.empty)((N, H, W, Cp), device=self.device, dtype=dtype)
             self.prog.bytes += t.numel() * t.element_size()
-        return View(t)
+        return View(t, 0, Cc)
 
     def release(self, *views):
         for v in views:
@@ -181,6 +208,15 @@ class Builder:
         if out is None:
             out = self.alloc(x.N, Ho, Wo, pc.Cout, out_dtype)
         assert (out.N, out.H, out.W, out.C) == (x.N, Ho, Wo, pc.Cout), ((out.N, out.H, out.W, out.C), (x.N, Ho, Wo, pc.Cout))
+        use_tc = (self.tensor_cores and x.dtype == torch.bfloat16 and x.cstride % 8 == 0 and x.coff % 8 == 0
+                  and pc.Cin >= 16)
+        scaled = None
+        if use_tc and in_scale is not None:
+            # the TMA-fed A operand never passes through registers: apply the SE gate in a separate pass
+            scaled = self.alloc(x.N, x.H, x.W, x.C, x.dtype)
+            self.op("rgbd_scale_channels", x.ptr(), scaled.ptr(), _DT[x.dtype], in_scale.data_ptr(), x.N, x.H * x.W,
+                    x.C, x.cstride, x.coff, scaled.cstride, scaled.coff)
+            x, in_scale = scaled, None
         for ln in launches:
             d = L.ConvDesc()
             d.x, d.y, d.w = x.ptr(), out.ptr(), pc.w32.data_ptr()
@@ -212,13 +248,26 @@ class Builder:
             d.act, d.epi = act, epi
             d.x_dtype, d.y_dtype = _DT[x.dtype], _DT[out.dtype]
             d.cout_pad = pc.cout_pad
-            L.check(L.load().rgbd_conv_validate(C.byref(d)), "rgbd_conv_validate")
             self.prog.keep.append(d)
-            run = self.op("rgbd_conv_simt", C.byref(d))
+            if use_tc:
+                d.w = pc.wtc.data_ptr()
+                handle = C.c_void_p()
+                L.check(L.load().rgbd_conv_tc_plan_create(C.byref(d), pc.cin_pad, C.byref(handle)),
+                        "rgbd_conv_tc_plan_create")
+                self.prog.tc_plans.append(handle)
+                run = self.op("rgbd_conv_tc_run", handle)
+                self.prog.n_tc += 1
+            else:
+                L.check(L.load().rgbd_conv_validate(C.byref(d)), "rgbd_conv_validate")
+                run = self.op("rgbd_conv_simt", C.byref(d))
+                self.prog.n_simt += 1
             run.is_conv = True
+            run.is_tc = use_tc
             run.flops = 2 * x.N * ln["Hs"] * ln["Ws"] * len(ln["taps"]) * pc.Cin * pc.Cout
             self.prog.flops += run.flops
         self.prog.keep.extend([pc, x.buf, out.buf])
+        if scaled is not None:
+            self.release(scaled)
         return out
 
     def se_scale(self, x, w1, w2, plus_one):

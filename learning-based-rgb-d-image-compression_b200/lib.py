@@ -60,6 +60,7 @@ _PROTOS = {
     "rgbd_maxpool7s3": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_nchw_to_nhwc": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_nhwc_to_nchw": [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "rgbd_scale_channels": [_vp, _vp, _i32, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_copy_view": [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_zero": [_vp, _i64, _vp],
     "rgbd_ckbd_quantize_index": [_vp, _i32, _i32, _vp, _vp, _i32, _f32, _i32, _i32, _i32, _i32, _i32, _vp, _vp,

@@ -266,3 +266,111 @@ def test_likelihood_kernels_vs_torch():
     torch.cuda.synchronize()
     assert torch.allclose(lz.cpu(), lz_want, atol=1e-5, rtol=1e-4)
     assert torch.allclose(zhat.cpu().reshape(B, 4, 5, 192).permute(0, 3, 1, 2), zh_want, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 tensor-core conv path (bf16 operands, fp32 TMEM accumulators) vs torch CPU on the same
+# bf16-rounded inputs and weights.  fp32 outputs: tolerance 1e-3 of the tensor scale (accumulation
+# order / tensor-core fp32 accumulate); bf16 outputs: + one bf16 rounding (2^-8).
+# ------------------------------------------------------------------------------------------------
+def run_conv_tc(mod, x_nchw, tensor_cores=True, out_dtype=torch.float32, **kw):
+    from rgbd_b200.engine import Builder, PackedConv, View
+    b = Builder(torch.device(DEV), torch.bfloat16, tensor_cores=tensor_cores)
+
+    def view(t, pad=8):
+        if t is None:
+            return None
+        nhwc = t.permute(0, 2, 3, 1).contiguous()
+        Cp = (nhwc.shape[3] + 7) // 8 * 8 + 2 * pad
+        buf = torch.zeros(*nhwc.shape[:3], Cp, device=DEV, dtype=torch.bfloat16)
+        buf[..., pad:pad + nhwc.shape[3]] = nhwc.to(DEV).to(torch.bfloat16)
+        return View(buf, pad, nhwc.shape[3])
+
+    pc = PackedConv(mod, torch.device(DEV))
+    args = {k: (view(v) if k in ("res", "mul") else v) for k, v in kw.items()}
+    if "in_scale" in args:
+        args["in_scale"] = args["in_scale"].to(DEV)
+    out = b.conv(pc, view(x_nchw), out_dtype=out_dtype, **args)
+    assert (b.prog.n_tc > 0) == tensor_cores, (b.prog.n_tc, b.prog.n_simt)
+    b.prog.run()
+    torch.cuda.synchronize()
+    return out.torch().float().cpu().permute(0, 3, 1, 2)
+
+
+def bf16_ref(mod, x):
+    m = type(mod)(mod.in_channels, mod.out_channels, mod.kernel_size, mod.stride, mod.padding,
+                  **({"output_padding": mod.output_padding} if isinstance(mod, nn.ConvTranspose2d) else {})).eval()
+    with torch.no_grad():
+        m.weight.copy_(mod.weight.bfloat16().float())
+        m.bias.copy_(mod.bias)
+        return m(x.bfloat16().float())
+
+
+TC_CONVS = [
+    ("1x1_192_96", lambda: nn.Conv2d(192, 96, 1), (2, 192, 32, 40)),
+    ("3x3_96_96_ragged", lambda: nn.Conv2d(96, 96, 3, 1, 1), (2, 96, 19, 21)),
+    ("5x5s2_384_192", lambda: nn.Conv2d(384, 192, 5, 2, 2), (1, 384, 32, 48)),
+    ("5x5s2_odd_hw", lambda: nn.Conv2d(64, 64, 5, 2, 2), (1, 64, 17, 23)),
+    ("3x3s2p0_48", lambda: nn.Conv2d(48, 48, 3, 2, 0), (1, 48, 33, 41)),
+    ("5x5_ctx_16_32", lambda: nn.Conv2d(16, 32, 5, 1, 2), (2, 16, 32, 40)),
+    ("1x1_1344_224", lambda: nn.Conv2d(1344, 224, 1), (1, 1344, 8, 12)),
+    ("3x3_213_42_oddC", lambda: nn.Conv2d(213, 42, 3, 1, 1), (1, 213, 16, 20)),
+    ("5x5_512_384", lambda: nn.Conv2d(512, 384, 5, 1, 2), (1, 512, 8, 10)),
+    ("deconv5s2_192", lambda: nn.ConvTranspose2d(192, 192, 5, 2, padding=2, output_padding=1), (1, 192, 9, 11)),
+    ("deconv5s2_to3", lambda: nn.ConvTranspose2d(192, 3, 5, 2, padding=2, output_padding=1), (2, 192, 16, 16)),
+    ("deconv3s1_960_640", lambda: nn.ConvTranspose2d(960, 640, 3, 1, padding=1), (1, 960, 8, 10)),
+]
+
+
+@pytest.mark.parametrize("name,make,shape", TC_CONVS, ids=[c[0] for c in TC_CONVS])
+def test_conv_tc_vs_torch(name, make, shape):
+    torch.manual_seed(11)
+    mod = make().eval()
+    x = torch.randn(shape)
+    want = bf16_ref(mod, x)
+    got = run_conv_tc(mod, x)
+    assert got.shape == want.shape
+    assert rel_err(got, want) < 1e-3, (name, rel_err(got, want))
+    # the CUDA-core kernel on the same bf16 activations (it keeps fp32 weights)
+    simt = run_conv_tc(mod, x, tensor_cores=False)
+    with torch.no_grad():
+        assert rel_err(simt, mod(x.bfloat16().float())) < 2e-4
+    got16 = run_conv_tc(mod, x, out_dtype=torch.bfloat16)
+    assert rel_err(got16, want) < 6e-3, name
+
+
+def test_conv_tc_epilogues():
+    torch.manual_seed(12)
+    mod = nn.Conv2d(96, 192, 1).eval()
+    x, res, mul = torch.randn(2, 96, 10, 12), torch.randn(2, 192, 10, 12), torch.randn(2, 192, 10, 12)
+    rb, mb = res.bfloat16().float(), mul.bfloat16().float()
+    v = bf16_ref(mod, x)
+    tol = 1e-3
+    assert rel_err(run_conv_tc(mod, x, act=1), F.relu(v)) < tol
+    assert rel_err(run_conv_tc(mod, x, act=2), F.leaky_relu(v)) < tol
+    assert rel_err(run_conv_tc(mod, x, act=1, res=res), F.relu(v + rb)) < tol
+    assert rel_err(run_conv_tc(mod, x, epi=1, mul=mul, res=res), rb + mb * torch.sigmoid(v)) < tol
+    assert rel_err(run_conv_tc(mod, x, epi=1, mul=mul), mb * torch.sigmoid(v)) < tol
+    # SE gate folded through the separate scale pass (bf16 rounding of the scaled input)
+    scale = torch.rand(2, 96) + 0.5
+    want = bf16_ref(mod, (x.bfloat16().float() * scale[:, :, None, None]))
+    assert rel_err(run_conv_tc(mod, x, in_scale=scale), want) < 1e-2
+    mod2 = nn.Conv2d(48, 48, 1).eval()
+    x2 = torch.randn(2, 48, 37, 45)
+    for small in ((2, 48, 5, 7), (2, 48, 11, 13)):
+        sm = torch.randn(small)
+        want = bf16_ref(mod2, x2) + F.interpolate(sm.bfloat16().float(), (37, 45), mode="bilinear", align_corners=False)
+        assert rel_err(run_conv_tc(mod2, x2, epi=2, res=sm), want) < tol, small
+
+
+def test_conv_tc_is_deterministic_and_batch_invariant():
+    """Same pixels -> same bits, whatever the batch size / tile position."""
+    torch.manual_seed(13)
+    mod = nn.Conv2d(128, 64, 3, 1, 1).eval()
+    x = torch.randn(3, 128, 24, 40)
+    full = run_conv_tc(mod, x, out_dtype=torch.float32)
+    again = run_conv_tc(mod, x, out_dtype=torch.float32)
+    assert torch.equal(full, again)
+    for i in range(3):
+        one = run_conv_tc(mod, x[i:i + 1], out_dtype=torch.float32)
+        assert torch.equal(one[0], full[i])
