@@ -284,10 +284,13 @@ rans_decode_kernel(const uint32_t *__restrict__ words, const int64_t *__restrict
             if (value == L - 2) {  // escape bin: bypass nibbles (rans_interface.cpp:323-344)
                 int32_t d = (int32_t)dec_get4(x, pos, feed, lane);
                 int32_t nnib = d;
-                while (d == 15) {
+                // valid streams carry at most 8 payload nibbles, so the unary count never continues;
+                // the bounds only stop a corrupt stream from spinning
+                for (int guard = 0; d == 15 && guard < 4; ++guard) {
                     d = (int32_t)dec_get4(x, pos, feed, lane);
                     nnib += d;
                 }
+                if (nnib > 64) nnib = 64;
                 int32_t raw = 0;
                 for (int k = 0; k < nnib; ++k) {
                     d = (int32_t)dec_get4(x, pos, feed, lane);

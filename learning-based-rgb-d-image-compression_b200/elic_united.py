@@ -473,8 +473,8 @@ class ELIC_united(nn.Module):
         in_r = b.raw((B, 3, H, W), torch.float32)
         in_d = b.raw((B, 1, H, W), torch.float32)
         p.io["rgb"], p.io["depth"] = in_r, in_d
-        b.op("rgbd_nchw_to_nhwc", in_r.data_ptr(), x_r.ptr(), _DT[x_r.dtype], B, 3, H, W, 3, 0)
-        b.op("rgbd_nchw_to_nhwc", in_d.data_ptr(), x_d.ptr(), _DT[x_d.dtype], B, 1, H, W, 1, 0)
+        b.op("rgbd_nchw_to_nhwc", in_r.data_ptr(), x_r.ptr(), _DT[x_r.dtype], B, 3, H, W, x_r.cstride, x_r.coff)
+        b.op("rgbd_nchw_to_nhwc", in_d.data_ptr(), x_d.ptr(), _DT[x_d.dtype], B, 1, H, W, x_d.cstride, x_d.coff)
         y_r, y_d = self._transform(b, self.g_a.rgb_analysis_transform, self.g_a.depth_analysis_transform,
                                    x_r, x_d, final_dtype=torch.float32)
         z_r, z_d = self._h_a(b, y_r, y_d)

@@ -116,7 +116,7 @@ def run_conv(mod, x_nchw, act=0, epi=0, res=None, mul=None, in_scale=None, dtype
              pad_c=0):
     """Runs one nn.Conv2d / ConvTranspose2d through engine.Builder (-> rgbd_conv_simt)."""
     from rgbd_b200.engine import Builder, PackedConv, View
-    b = Builder(torch.device(DEV), dtype)
+    b = Builder(torch.device(DEV), dtype, tensor_cores=False)
 
     def view(t):
         if t is None:
