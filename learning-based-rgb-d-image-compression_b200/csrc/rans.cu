@@ -80,22 +80,33 @@ __device__ __forceinline__ void enc_put_bits4(EncState &st, uint32_t val, uint32
     st.x = (st.x << 4) | val;
 }
 
+// Per-symbol record staged in shared memory by the lane that prepared it; the serial chain reads it
+// back as a broadcast (prefetched one symbol ahead, so the LDS latency is off the x chain).
+struct __align__(16) EncRec {
+    uint64_t rcp;     // exact reciprocal of range; ~0 for range == 1 (rans64.h:191-210)
+    uint32_t bias;    // start (+ 65535 for range == 1)
+    uint32_t packed;  // range | rcp_shift << 16
+};
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 rans_encode_kernel(const int32_t *__restrict__ sym, const uint8_t *__restrict__ idx,
                    int64_t stream_stride, int32_t n_sym, int32_t n_streams, rgbd_rans_tables t,
                    uint32_t *__restrict__ out, int64_t cap_words, int32_t *__restrict__ nwords) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ EncRec s_rec[kWarpsPerBlock][32];
     TableSmem &meta = *reinterpret_cast<TableSmem *>(smem_raw);
     uint16_t *s_cdf = reinterpret_cast<uint16_t *>(smem_raw + sizeof(TableSmem));
     load_tables(t, s_cdf, meta);
 
     const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int wib = threadIdx.x >> 5;
+    const int s = blockIdx.x * kWarpsPerBlock + wib;
     if (s >= n_streams) return;
 
     const int32_t *my_sym = sym + (int64_t)s * stream_stride;
     const uint8_t *my_idx = idx + (int64_t)s * stream_stride;
     uint32_t *out_base = out + (int64_t)s * cap_words;
+    EncRec *rec = s_rec[wib];
 
     EncState st;
     st.x = kRansL;
@@ -117,7 +128,7 @@ rans_encode_kernel(const int32_t *__restrict__ sym, const uint8_t *__restrict__ 
             pf_idx = my_idx[i - 32];
         }
         EncSym e;
-        e.rcp = 0; e.start = 0; e.range = 2; e.rcp_shift = 0; e.raw = 0; e.esc = 0;
+        e.rcp = ~0ull; e.start = 0; e.range = 1; e.rcp_shift = 0; e.raw = 0; e.esc = 0;
         if (i >= 0) {
             const int32_t top = meta.length[ti] - 2;
             int32_t v = cur_sym - meta.offset[ti];
@@ -138,6 +149,28 @@ rans_encode_kernel(const int32_t *__restrict__ sym, const uint8_t *__restrict__ 
             if (e.range >= 2) make_reciprocal(e.range, e.rcp, e.rcp_shift);
         }
         const int nvalid = hi < 32 ? hi : 32;
+        const uint32_t any_esc = __ballot_sync(0xffffffffu, e.esc != 0);
+        if (any_esc == 0) {
+            // ---- fast path: no escape symbol in this batch ----
+            EncRec mine;
+            mine.rcp = e.rcp;
+            mine.bias = e.range >= 2 ? e.start : e.start + 65535u;   // range 1: q = x - 1 (rans64.h:191-210)
+            mine.packed = e.range | (e.rcp_shift << 16);
+            rec[lane] = mine;
+            __syncwarp();
+            EncRec cur = rec[0];
+            for (int j = 0; j < nvalid; ++j) {
+                const EncRec nxt = rec[(j + 1) & 31];
+                const uint32_t range = cur.packed & 0xFFFFu;
+                // Rans64EncPut (rans64.h:77-93): x_max = ((L >> 16) << 32) * range
+                if (st.x >= ((uint64_t)range << 47)) enc_emit(st, out_base, lane);
+                const uint64_t q = __umul64hi(st.x, cur.rcp) >> (cur.packed >> 16);   // == x / range (exact)
+                st.x = st.x + cur.bias + q * (uint64_t)(65536u - range);
+                cur = nxt;
+            }
+            __syncwarp();
+            continue;
+        }
         for (int j = 0; j < nvalid; ++j) {
             const uint32_t esc = __shfl_sync(0xffffffffu, e.esc, j);
             if (esc) {  // warp-uniform; rare
@@ -153,7 +186,6 @@ rans_encode_kernel(const int32_t *__restrict__ sym, const uint8_t *__restrict__ 
             const uint32_t start = __shfl_sync(0xffffffffu, e.start, j);
             const uint32_t rshift = __shfl_sync(0xffffffffu, e.rcp_shift, j);
             const uint64_t rcp = __shfl_sync(0xffffffffu, (unsigned long long)e.rcp, j);
-            // Rans64EncPut (rans64.h:77-93): x_max = ((L >> 16) << 32) * range
             if (st.x >= ((uint64_t)range << 47)) enc_emit(st, out_base, lane);
             if (range >= 2) {
                 const uint64_t q = __umul64hi(st.x, rcp) >> rshift;  // == x / range (exact)
@@ -204,17 +236,6 @@ struct WordFeed {
     }
 };
 
-__device__ __forceinline__ uint32_t dec_get4(uint64_t &x, int64_t &pos, WordFeed &feed, int lane) {
-    // Rans64DecGetBits with n_bits = 4 (rans_interface.cpp:80-96)
-    const uint32_t v = (uint32_t)(x & 15u);
-    x >>= 4;
-    if (x < kRansL) {
-        x = (x << 32) | feed.take(pos, lane);
-        pos += 1;
-    }
-    return v;
-}
-
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 rans_decode_kernel(const uint32_t *__restrict__ words, const int64_t *__restrict__ word_off,
                    const int64_t *__restrict__ word_len, int32_t n_streams,
@@ -222,43 +243,45 @@ rans_decode_kernel(const uint32_t *__restrict__ words, const int64_t *__restrict
                    int32_t *__restrict__ sym, int64_t stream_stride, int64_t chunk_off,
                    int32_t n_sym, rgbd_rans_tables t) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int4 s_meta[kWarpsPerBlock][32];   // (base, length, offset, -) of the batch's tables
     TableSmem &meta = *reinterpret_cast<TableSmem *>(smem_raw);
     uint16_t *s_cdf = reinterpret_cast<uint16_t *>(smem_raw + sizeof(TableSmem));
     load_tables(t, s_cdf, meta);
 
     const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int wib = threadIdx.x >> 5;
+    const int s = blockIdx.x * kWarpsPerBlock + wib;
     if (s >= n_streams) return;
 
     uint64_t x = state[s].x;
     int64_t pos = state[s].pos;
     WordFeed feed;
     feed.init(words + word_off[s], word_len[s], pos, lane);
+    uint32_t wnext = feed.take(pos, lane);   // the word a renormalisation would consume next
 
     const uint8_t *my_idx = idx + (int64_t)s * stream_stride + chunk_off;
     int32_t *my_sym = sym + (int64_t)s * stream_stride + chunk_off;
+    int4 *mrow = s_meta[wib];
 
     int32_t pf_idx = (lane < n_sym) ? (int32_t)my_idx[lane] : 0;  // prefetched one batch early
     for (int32_t lo_i = 0; lo_i < n_sym; lo_i += 32) {
         const int32_t i = lo_i + lane;
         const int32_t ti = pf_idx;
         if (i + 32 < n_sym) pf_idx = my_idx[i + 32];
-        int32_t tb = 0, tl = 2, to = 0;
-        if (i < n_sym) {
-            tb = meta.base[ti];
-            tl = meta.length[ti];
-            to = meta.offset[ti];
-        }
+        int4 mine = make_int4(0, 2, 0, 0);
+        if (i < n_sym) mine = make_int4(meta.base[ti], meta.length[ti], meta.offset[ti], 0);
+        mrow[lane] = mine;
+        __syncwarp();
         int32_t my_out = 0;
         const int nvalid = (n_sym - lo_i) < 32 ? (n_sym - lo_i) : 32;
+        int4 cur = mrow[0];
         for (int j = 0; j < nvalid; ++j) {
-            const int32_t b = __shfl_sync(0xffffffffu, tb, j);
-            const int32_t L = __shfl_sync(0xffffffffu, tl, j);
-            const int32_t off = __shfl_sync(0xffffffffu, to, j);
+            const int4 nxt = mrow[(j + 1) & 31];
+            const int32_t b = cur.x, L = cur.y, off = cur.z;
             const uint32_t cf = (uint32_t)(x & 0xFFFFu);  // Rans64DecGet
-            // find s_ = (first k with cdf[k] > cf) - 1; invariant cdf[lo] <= cf < cdf[hi]
-            int32_t lo = 0, hi = L - 1;  // cdf[L-1] == 65536 (stored as 0)
-            while (hi - lo > 31) {
+            // invariant cdf[lo] <= cf < cdf[hi]; cdf[L-1] == 65536 (stored as 0)
+            int32_t lo = 0, hi = L - 1;
+            while (hi - lo > 31) {   // only tables with more than 32 entries
                 const int32_t stride = (hi - lo + 31) >> 5;
                 const int32_t p = lo + (lane + 1) * stride;
                 const bool above = (p >= hi) || (s_cdf[b + p] > cf);
@@ -268,32 +291,45 @@ rans_decode_kernel(const uint32_t *__restrict__ words, const int64_t *__restrict
                 lo = lo + f * stride;
                 hi = nhi < hi ? nhi : hi;
             }
+            // every lane tests the hypothesis "the symbol is lo + lane" and pre-computes the state
+            // that hypothesis leads to (Rans64DecAdvance, rans64.h:126-142); exactly one lane is right
             const int32_t p = lo + lane;
-            const uint32_t val = (p >= L - 1) ? 65536u : (uint32_t)s_cdf[b + p];
-            const uint32_t m = __ballot_sync(0xffffffffu, val > cf);
-            const int f = __ffs(m) - 1;  // f >= 1 because cdf[lo] <= cf
-            const uint32_t c1 = __shfl_sync(0xffffffffu, val, f);
-            const uint32_t c0 = __shfl_sync(0xffffffffu, val, f - 1);
-            int32_t value = lo + f - 1;
-            // Rans64DecAdvance (rans64.h:126-142)
-            x = (uint64_t)(c1 - c0) * (x >> 16) + cf - c0;
+            const uint32_t c0 = (p >= L - 1) ? 65536u : (uint32_t)s_cdf[b + p];
+            const uint32_t c1 = (p + 1 >= L - 1) ? 65536u : (uint32_t)s_cdf[b + p + 1];
+            const bool hit = (c0 <= cf) && (cf < c1);
+            const uint64_t xh = (uint64_t)(c1 - c0) * (x >> 16) + (uint64_t)(cf - c0);
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            const int f = __ffs(m) - 1;
+            x = __shfl_sync(0xffffffffu, (unsigned long long)xh, f);
+            int32_t value = lo + f;
             if (x < kRansL) {
-                x = (x << 32) | feed.take(pos, lane);
+                x = (x << 32) | wnext;
                 pos += 1;
+                wnext = feed.take(pos, lane);
             }
             if (value == L - 2) {  // escape bin: bypass nibbles (rans_interface.cpp:323-344)
-                int32_t d = (int32_t)dec_get4(x, pos, feed, lane);
+                auto get4 = [&]() -> int32_t {
+                    const uint32_t v = (uint32_t)(x & 15u);
+                    x >>= 4;
+                    if (x < kRansL) {
+                        x = (x << 32) | wnext;
+                        pos += 1;
+                        wnext = feed.take(pos, lane);
+                    }
+                    return (int32_t)v;
+                };
+                int32_t d = get4();
                 int32_t nnib = d;
                 // valid streams carry at most 8 payload nibbles, so the unary count never continues;
                 // the bounds only stop a corrupt stream from spinning
                 for (int guard = 0; d == 15 && guard < 4; ++guard) {
-                    d = (int32_t)dec_get4(x, pos, feed, lane);
+                    d = get4();
                     nnib += d;
                 }
                 if (nnib > 64) nnib = 64;
                 int32_t raw = 0;
                 for (int k = 0; k < nnib; ++k) {
-                    d = (int32_t)dec_get4(x, pos, feed, lane);
+                    d = get4();
                     if (k < 8) raw |= d << (k * 4);
                 }
                 value = raw >> 1;
@@ -301,7 +337,9 @@ rans_decode_kernel(const uint32_t *__restrict__ words, const int64_t *__restrict
                 else value += L - 2;
             }
             if (lane == j) my_out = value + off;
+            cur = nxt;
         }
+        __syncwarp();
         if (i < n_sym) my_sym[i] = my_out;
     }
     if (lane == 0) {

@@ -497,17 +497,21 @@ class ELIC_united(nn.Module):
         zs = {"r": z_r, "d": z_d}
         offs, ny = self._chunk_offsets(h, w)
         st = {}
-        for which in ("r", "d"):
+        # both modalities' y streams live in one [2B, ...] buffer so one launch can code all of them
+        ycap = ny + ny // 2 + 64
+        ysym_all, yidx_all = b.raw((2 * B, ny), torch.int32), b.raw((2 * B, ny), torch.uint8)
+        yout_all, ynw_all = b.raw((2 * B, ycap), torch.int32), b.raw((2 * B,), torch.int32)
+        for k, which in enumerate(("r", "d")):
             eb = self._eb(which)
             med = self._dev32(("med", which), eb.medians)
             s = dict(
                 zsym=b.raw((B, nz), torch.int32), zidx=b.raw((B, nz), torch.uint8),
-                ysym=b.raw((B, ny), torch.int32), yidx=b.raw((B, ny), torch.uint8),
-                zcap=nz + nz // 2 + 64, ycap=ny + ny // 2 + 64)
+                ysym=ysym_all[k * B:(k + 1) * B], yidx=yidx_all[k * B:(k + 1) * B],
+                zcap=nz + nz // 2 + 64, ycap=ycap)
             s["zout"] = b.raw((B, s["zcap"]), torch.int32)
-            s["yout"] = b.raw((B, s["ycap"]), torch.int32)
+            s["yout"] = yout_all[k * B:(k + 1) * B]
             s["znw"] = b.raw((B,), torch.int32)
-            s["ynw"] = b.raw((B,), torch.int32)
+            s["ynw"] = ynw_all[k * B:(k + 1) * B]
             st[which] = s
             zh = zcat.sub(0 if which == "r" else Nz, Nz)
             b.op("rgbd_eb_quantize", zs[which].ptr(), zs[which].cstride, B, hz * wz, Nz, med.data_ptr(),
@@ -534,12 +538,20 @@ class ELIC_united(nn.Module):
                  yhat[which].ptr(), _DT[yhat[which].dtype], yhat[which].cstride, coff)
 
         self._context_chain(b, ctx, ctx_rgb, yhat["r"], yhat["d"], code_step)
-        for which in ("r", "d"):
-            s = st[which]
-            t = self._tables("gc", which)
-            b.op("rgbd_rans_encode", s["ysym"].data_ptr(), s["yidx"].data_ptr(), ny, ny, B, ctypes.byref(t.struct),
-                 s["yout"].data_ptr(), s["ycap"], s["ynw"].data_ptr())
+        gr, gd = self._gc("r"), self._gc("d")
+        same_tables = all(torch.equal(getattr(gr, n), getattr(gd, n)) for n in ("_quantized_cdf", "_cdf_length", "_offset"))
+        if same_tables:   # the usual case: both Gaussian conditionals use get_scale_table()
+            t = self._tables("gc", "r")
+            b.op("rgbd_rans_encode", ysym_all.data_ptr(), yidx_all.data_ptr(), ny, ny, 2 * B, ctypes.byref(t.struct),
+                 yout_all.data_ptr(), ycap, ynw_all.data_ptr())
             p.keep.append(t)
+        else:
+            for which in ("r", "d"):
+                s = st[which]
+                t = self._tables("gc", which)
+                b.op("rgbd_rans_encode", s["ysym"].data_ptr(), s["yidx"].data_ptr(), ny, ny, B, ctypes.byref(t.struct),
+                     s["yout"].data_ptr(), s["ycap"], s["ynw"].data_ptr())
+                p.keep.append(t)
         p.io.update(st=st, shape=(hz, wz), y=ys, z=zs, yhat=yhat, ny=ny, nz=nz)
         return p
 
@@ -658,8 +670,8 @@ class ELIC_united(nn.Module):
         p.io.update(out_r=out_r, out_d=out_d, lik=lik, y=ys, z=zs, yhat=yhat)
         return p
 
-    def _program(self, kind, *dims):
-        key = (kind, self.precision, self.tensor_cores) + tuple(dims)
+    def _program(self, kind, *dims, slot=0):
+        key = (kind, self.precision, self.tensor_cores, slot) + tuple(dims)
         if key not in self._programs:
             self._require_cuda()
             with torch.cuda.device(self.device), torch.no_grad():
@@ -702,21 +714,41 @@ class ELIC_united(nn.Module):
 
     @torch.no_grad()
     def compress(self, rgb, depth):
+        return self.compress_async(rgb, depth).result()
+
+    @torch.no_grad()
+    def compress_async(self, rgb, depth, slot=0):
+        """Enqueue one compress() on pipeline slot `slot` (its own program instance and CUDA stream)
+        and return a handle; `.result()` waits for that slot only and returns the compress() dict.
+        Several slots in flight let the serial rANS kernels of one batch overlap the convolutions of
+        another (images are independent: SURVEY §8e)."""
         self._check_inputs(rgb, depth)
         B, _, H, W = rgb.shape
-        p = self._program("encoder", B, H, W)
-        with torch.cuda.device(self.device):
-            p.io["rgb"].copy_(rgb)
-            p.io["depth"].copy_(depth)
+        p = self._program("encoder", B, H, W, slot=slot)
+        stream = self._slot_stream(slot)
+        with torch.cuda.device(self.device), torch.cuda.stream(stream):
+            p.io["rgb"].copy_(rgb, non_blocking=True)
+            p.io["depth"].copy_(depth, non_blocking=True)
             p.run(self.use_cuda_graph)
-            strings = self._collect_strings(p, B)
-        return {"r_strings": [strings["ry"], strings["rz"]], "d_strings": [strings["dy"], strings["dz"]],
-                "shape": torch.Size(p.io["shape"])}
+            st = p.io["st"]
+            counts = torch.stack([st["r"]["ynw"], st["r"]["znw"], st["d"]["ynw"], st["d"]["znw"]])
+            counts_host = p.io.setdefault("counts_host", torch.empty((4, B), dtype=torch.int32).pin_memory())
+            counts_host.copy_(counts, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(stream)
+        return _CompressHandle(self, p, B, stream, done, counts_host)
 
-    def _collect_strings(self, p, B):
-        """One small D2H for the word counts, one packed D2H for all stream tails."""
+    def _slot_stream(self, slot):
+        if slot == 0:
+            return torch.cuda.current_stream(self.device)
+        streams = self.__dict__.setdefault("_slot_streams", {})
+        if slot not in streams:
+            streams[slot] = torch.cuda.Stream(self.device)
+        return streams[slot]
+
+    def _collect_strings(self, p, B, counts):
+        """One packed D2H for all stream tails (the word counts are already on the host)."""
         st = p.io["st"]
-        counts = torch.stack([st["r"]["ynw"], st["r"]["znw"], st["d"]["ynw"], st["d"]["znw"]]).cpu().numpy()
         if (counts < 0).any():
             raise L.RgbdError("rANS output buffer overflow (stream longer than 48 bits/symbol)")
         pieces, meta = [], []
@@ -739,13 +771,22 @@ class ELIC_united(nn.Module):
         self._require_cuda()
         torch.cuda.synchronize(self.device)
         t0 = time.process_time()
+        out = self.decompress_async(rgb_strings, depth_strings, shape).result()
+        torch.cuda.synchronize(self.device)
+        out["cost_time"] = time.process_time() - t0
+        return out
+
+    @torch.no_grad()
+    def decompress_async(self, rgb_strings, depth_strings, shape, slot=0):
+        """Enqueue one decompress() on pipeline slot `slot`; `.result()` returns {"x_hat": ...}."""
+        self._require_cuda()
         rz, dz = list(rgb_strings[1]), list(depth_strings[1])
         B = len(rz)
         ry, dy = list(rgb_strings[0]), list(depth_strings[0])
         if len(ry) != B or len(dy) != B or len(dz) != B:
             raise ValueError(f"expected {B} y strings per modality (one per image), got {len(ry)} / {len(dy)}")
         hz, wz = int(shape[0]), int(shape[1])
-        p = self._program("decoder", B, hz, wz)
+        p = self._program("decoder", B, hz, wz, slot=slot)
         streams = rz + dz + ry + dy
         lens = np.array([len(s) // 4 for s in streams], dtype=np.int64)
         if any(len(s) % 4 or len(s) < 8 for s in streams):
@@ -755,12 +796,56 @@ class ELIC_united(nn.Module):
         total = int(lens.sum())
         if total > p.io["words_cap"]:
             raise ValueError("streams larger than the decoder's word buffer")
-        blob = np.frombuffer(b"".join(streams), dtype=np.int32)
-        with torch.cuda.device(self.device):
-            p.io["words"][:total].copy_(torch.from_numpy(blob.copy()))
-            p.io["word_off"].copy_(torch.from_numpy(offs))
-            p.io["word_len"].copy_(torch.from_numpy(lens))
+        if "words_host" not in p.io:   # pinned staging so the H2D copies are asynchronous
+            p.io["words_host"] = torch.empty(p.io["words_cap"], dtype=torch.int32).pin_memory()
+            p.io["meta_host"] = torch.empty((2, 4 * B), dtype=torch.int64).pin_memory()
+        stream = self._slot_stream(slot)
+        with torch.cuda.device(self.device), torch.cuda.stream(stream):
+            prev = p.io.get("h2d_done")
+            if prev is not None:
+                prev.synchronize()     # the staging buffers are free again
+            wh = p.io["words_host"].numpy()
+            pos = 0
+            for sbytes in streams:
+                n = len(sbytes) // 4
+                wh[pos:pos + n] = np.frombuffer(sbytes, dtype=np.int32)
+                pos += n
+            p.io["meta_host"][0].copy_(torch.from_numpy(offs))
+            p.io["meta_host"][1].copy_(torch.from_numpy(lens))
+            p.io["words"][:total].copy_(p.io["words_host"][:total], non_blocking=True)
+            p.io["word_off"].copy_(p.io["meta_host"][0], non_blocking=True)
+            p.io["word_len"].copy_(p.io["meta_host"][1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            p.io["h2d_done"] = ev
             p.run(self.use_cuda_graph)
-            out_r, out_d = p.io["out_r"].clone(), p.io["out_d"].clone()
-            torch.cuda.synchronize(self.device)
-        return {"x_hat": {"r": out_r, "d": out_d}, "cost_time": time.process_time() - t0}
+            done = torch.cuda.Event()
+            done.record(stream)
+        return _DecompressHandle(p, stream, done)
+
+
+class _CompressHandle:
+    def __init__(self, net, prog, B, stream, done, counts_host):
+        self.net, self.prog, self.B, self.stream, self.done, self.counts_host = net, prog, B, stream, done, counts_host
+
+    def result(self):
+        self.done.synchronize()
+        p = self.prog
+        with torch.cuda.device(self.net.device), torch.cuda.stream(self.stream):
+            strings = self.net._collect_strings(p, self.B, self.counts_host.numpy().copy())
+        return {"r_strings": [strings["ry"], strings["rz"]], "d_strings": [strings["dy"], strings["dz"]],
+                "shape": torch.Size(p.io["shape"])}
+
+
+class _DecompressHandle:
+    def __init__(self, prog, stream, done):
+        self.prog, self.stream, self.done = prog, stream, done
+
+    def result(self, clone=True):
+        self.done.synchronize()
+        r, d = self.prog.io["out_r"], self.prog.io["out_d"]
+        if clone:
+            with torch.cuda.stream(self.stream):
+                r, d = r.clone(), d.clone()
+            self.stream.synchronize()
+        return {"x_hat": {"r": r, "d": d}}
