@@ -208,6 +208,10 @@ typedef struct rgbd_rans_tables {
     const int32_t *offset;  /* device [n_tables] = _offset */
     int32_t n_tables;
     int32_t total;          /* sum(length) */
+    /* device [total] x 16 B, encoder only: per CDF bin {u64 rcp, u32 bias, u32 range | shift << 16},
+     * the exact-reciprocal form of Rans64EncSymbolInit (ryg_rans rans64.h:167-247), so that
+     * mulhi(x, rcp) >> shift == x / range on the serial chain.  Built once per table set on the host. */
+    const void *enc_rec;
 } rgbd_rans_tables;
 
 /* BufferedRansEncoder.encode_with_indexes + flush (rans_interface.cpp:99-192), and

@@ -190,11 +190,13 @@ class Builder:
     # ---- ops ----
     def op(self, name, *args):
         fn = getattr(L.load(), name)
+        label = name
 
         def run(sp, fn=fn, args=args, name=name):
             rc = fn(*args, sp)
             if rc:
                 L.check(rc, name)
+        run.label = label
         self.prog.ops.append(run)
         return run
 
@@ -263,6 +265,8 @@ class Builder:
                 self.prog.n_simt += 1
             run.is_conv = True
             run.is_tc = use_tc
+            kind = ("deconv" if pc.transposed else "conv") + f"{pc.k}x{pc.k}" + (f"s{pc.stride}" if pc.stride > 1 else "")
+            run.label = f"{'tc' if use_tc else 'simt'} {kind} {pc.Cin}->{pc.Cout} @{ln['Hs']}x{ln['Ws']}"
             run.flops = 2 * x.N * ln["Hs"] * ln["Ws"] * len(ln["taps"]) * pc.Cin * pc.Cout
             self.prog.flops += run.flops
         self.prog.keep.extend([pc, x.buf, out.buf])

@@ -52,6 +52,28 @@ def pmf_to_quantized_cdf(pmf, precision=16):
     return torch.from_numpy(out.astype(np.int32))
 
 
+def encoder_records(flat_cdf, base, length):
+    """Per CDF bin the encoder's exact-reciprocal record {u64 rcp, u32 bias, u32 range | shift << 16}
+    (ryg_rans Rans64EncSymbolInit, rans64.h:167-247), computed with Python integers.
+    Returns int64 [total, 2] (16 bytes per bin, little endian)."""
+    total = int(flat_cdf.size)
+    out = np.zeros((total, 2), dtype=np.uint64)
+    for t in range(len(length)):
+        b, n = int(base[t]), int(length[t])
+        for v in range(n - 1):
+            start = int(flat_cdf[b + v])
+            rng = (int(flat_cdf[b + v + 1]) - start) & 0xFFFF     # uint16 cast of the reference
+            if rng >= 2:
+                s = (rng - 1).bit_length()                          # ceil(log2(range))
+                rcp = ((1 << (s + 63)) + rng - 1) // rng
+                shift, bias = s - 1, start
+            else:                                                   # range 1: q = mulhi(x, 2^64-1) = x - 1
+                rcp, shift, bias = (1 << 64) - 1, 0, start + 65535
+            out[b + v, 0] = rcp
+            out[b + v, 1] = bias | ((rng | (shift << 16)) << 32)
+    return out.view(np.int64)
+
+
 class DeviceTables:
     """Compacted uint16 CDF tables + (base, length, offset) resident on the device."""
 
@@ -67,8 +89,10 @@ class DeviceTables:
         self.base = torch.from_numpy(base).to(device)
         self.length = torch.from_numpy(length).to(device)
         self.offset = torch.from_numpy(off).to(device)
+        self.enc_rec = torch.from_numpy(encoder_records(flat, base, length)).to(device)
         self.struct = _lib.RansTables(self.cdf.data_ptr(), self.base.data_ptr(), self.length.data_ptr(),
-                                      self.offset.data_ptr(), int(len(length)), int(flat16.size))
+                                      self.offset.data_ptr(), int(len(length)), int(flat16.size),
+                                      self.enc_rec.data_ptr())
 
 
 class EntropyModelBase(nn.Module):

@@ -44,7 +44,7 @@ class ConvDesc(C.Structure):
 class RansTables(C.Structure):
     _fields_ = [
         ("cdf", C.c_void_p), ("base", C.c_void_p), ("length", C.c_void_p), ("offset", C.c_void_p),
-        ("n_tables", C.c_int32), ("total", C.c_int32),
+        ("n_tables", C.c_int32), ("total", C.c_int32), ("enc_rec", C.c_void_p),
     ]
 
 
