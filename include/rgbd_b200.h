@@ -114,7 +114,7 @@ void rgbd_conv_tc_plan_destroy(rgbd_conv_tc_plan *p);
  * Small spatial / channel ops of the transforms.
  * ------------------------------------------------------------------------------------------ */
 /* SE_Block (modules/transform/attention.py:52-67): s[n,c] = sigmoid(W2 relu(W1 mean_hw x)).
- * `partial` is a work buffer of N*nchunk*C floats; out scale[n,c] = s (+1 if plus_one, which
+ * `partial` is a work buffer of N*(nchunk*C + C + Cr) floats (partial sums, means, hidden); out scale[n,c] = s (+1 if plus_one, which
  * folds EntropyParametersEX's `x + se(x)`, modules/transform/entropy.py:75). Deterministic
  * fixed-order reduction, independent of N. */
 int rgbd_se_scale(const void *x, int32_t dtype, int32_t N, int32_t HW, int32_t C, int32_t cstride,
@@ -128,9 +128,11 @@ int rgbd_scale_channels(const void *x, void *y, int32_t dtype, const float *scal
 /* F.max_pool2d(kernel 7, stride 3) of ESA (attention.py:88) */
 int rgbd_maxpool7s3(const void *x, void *y, int32_t dtype, int32_t N, int32_t H, int32_t W,
                     int32_t C, void *stream);
-/* NCHW fp32 image -> NHWC (dtype), and back with optional clamp to [0,1] (elic_united.py:452) */
+/* NCHW fp32 image -> NHWC (dtype), and back with optional clamp to [0,1] (elic_united.py:452).
+ * split3 != 0 writes 3*C channels [hi | lo | hi] (hi = dtype(x), lo = dtype(x - hi)): the two-term
+ * bf16 expansion the tensor-core first layer consumes against weights packed [w_hi | w_hi | w_lo]. */
 int rgbd_nchw_to_nhwc(const float *x, void *y, int32_t dtype, int32_t N, int32_t C, int32_t H,
-                      int32_t W, int32_t y_cstride, int32_t y_coff, void *stream);
+                      int32_t W, int32_t y_cstride, int32_t y_coff, int32_t split3, void *stream);
 int rgbd_nhwc_to_nchw(const void *x, int32_t dtype, float *y, int32_t N, int32_t C, int32_t H,
                       int32_t W, int32_t x_cstride, int32_t x_coff, int32_t clamp01, void *stream);
 

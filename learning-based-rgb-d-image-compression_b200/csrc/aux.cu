@@ -22,34 +22,48 @@ __global__ void se_partial_kernel(const T *__restrict__ x, int HW, int C, int cs
     }
 }
 
-// one CTA per image: mean -> FC1 + ReLU -> FC2 + sigmoid (+1)
-__global__ void se_fc_kernel(const float *__restrict__ partial, int nchunk, int HW, int C,
-                             const float *__restrict__ w1, const float *__restrict__ w2, int Cr,
-                             int plus_one, float *__restrict__ scale) {
-    extern __shared__ float sm[];
-    float *mean = sm;        // [C]
-    float *hid = sm + C;     // [Cr]
-    const int n = blockIdx.x;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < nchunk; ++k) s += partial[((int64_t)n * nchunk + k) * C + c];
-        mean[c] = s / (float)HW;
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    for (int r = warp; r < Cr; r += nwarp) {
-        float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(w1[(int64_t)r * C + c], mean[c], s);
+// SE squeeze-excite MLP, spread over many CTAs (the one-CTA-per-image form was latency bound):
+//   se_mean_kernel   : mean[n][c]   = (sum of the partials in fixed order) / HW
+//   se_hidden_kernel : hid[n][r]    = relu(W1[r,:] . mean[n,:])          one warp per (n, r)
+//   se_gate_kernel   : scale[n][c]  = sigmoid(W2[c,:] . hid[n,:]) (+1)   one warp per (n, c)
+__global__ void se_mean_kernel(const float *__restrict__ partial, int nchunk, int HW, int N, int C,
+                               float *__restrict__ mean) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)N * C) return;
+    const int n = (int)(e / C), c = (int)(e % C);
+    float s = 0.f;
+    for (int k = 0; k < nchunk; ++k) s += partial[((int64_t)n * nchunk + k) * C + c];
+    mean[e] = s / (float)HW;
+}
+
+__global__ void se_hidden_kernel(const float *__restrict__ mean, const float *__restrict__ w1, int N, int C, int Cr,
+                                 float *__restrict__ hid) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= (int64_t)N * Cr) return;
+    const int n = (int)(wid / Cr), r = (int)(wid % Cr);
+    const float *m = mean + (int64_t)n * C, *w = w1 + (int64_t)r * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(w[c], m[c], s);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) hid[r] = s > 0.f ? s : 0.f;
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s = 0.f;
-        for (int r = 0; r < Cr; ++r) s = fmaf(w2[(int64_t)c * Cr + r], hid[r], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) hid[wid] = s > 0.f ? s : 0.f;
+}
+
+__global__ void se_gate_kernel(const float *__restrict__ hid, const float *__restrict__ w2, int N, int C, int Cr,
+                               int plus_one, float *__restrict__ scale) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= (int64_t)N * C) return;
+    const int n = (int)(wid / C), c = (int)(wid % C);
+    const float *h = hid + (int64_t)n * Cr, *w = w2 + (int64_t)c * Cr;
+    float s = 0.f;
+    for (int r = lane; r < Cr; r += 32) s = fmaf(w[r], h[r], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
         const float g = 1.0f / (1.0f + expf(-s));
-        scale[(int64_t)n * C + c] = plus_one ? 1.0f + g : g;
+        scale[wid] = plus_one ? 1.0f + g : g;
     }
 }
 
@@ -75,16 +89,26 @@ __global__ void maxpool7s3_kernel(const T *__restrict__ x, T *__restrict__ y, in
     }
 }
 
+// split3: write [hi | lo | hi] with hi = T(x), lo = T(x - hi): a two-term bf16 expansion of the fp32
+// image (exact for 16-bit depth), consumed by a first conv packed as [w_hi | w_hi | w_lo], i.e.
+// x*w ~= hi*w_hi + lo*w_hi + hi*w_lo, all inside the one K=16 MMA a tap costs anyway.
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float *__restrict__ x, T *__restrict__ y, int N, int C, int H, int W,
-                                    int cstride, int coff) {
+                                    int cstride, int coff, int split3) {
     const int64_t total = (int64_t)N * C * H * W;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t hw = e % ((int64_t)H * W);
         const int c = (int)((e / ((int64_t)H * W)) % C);
         const int n = (int)(e / ((int64_t)H * W * C));
-        ElemIO<T>::st(y + ((int64_t)n * H * W + hw) * cstride + coff + c, x[e]);
+        T *dst = y + ((int64_t)n * H * W + hw) * cstride + coff + c;
+        const float v = x[e];
+        ElemIO<T>::st(dst, v);
+        if (split3) {
+            const float hi = round_to<T>(v);
+            ElemIO<T>::st(dst + C, v - hi);
+            ElemIO<T>::st(dst + 2 * C, v);
+        }
     }
 }
 
@@ -179,7 +203,7 @@ extern "C" int rgbd_se_scale(const void *x, int32_t dtype, int32_t N, int32_t HW
                              float *partial, int32_t nchunk, float *scale, void *stream) {
     RGBD_CHECK_ARG(x && w1 && w2 && partial && scale, "null pointer");
     RGBD_CHECK_ARG(N > 0 && HW > 0 && C > 0 && Cr > 0 && nchunk > 0, "dims");
-    RGBD_CHECK_ARG((size_t)(C + Cr) * 4 <= 48 * 1024, "C too large for the FC kernel");
+
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)(N * nchunk), (unsigned)((C + 127) / 128));
     if (dtype == RGBD_DT_F32)
@@ -188,7 +212,14 @@ extern "C" int rgbd_se_scale(const void *x, int32_t dtype, int32_t N, int32_t HW
         se_partial_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16 *)x, HW, C, cstride, coff,
                                                                 nchunk, partial);
     RGBD_LAUNCH_CHECK();
-    se_fc_kernel<<<N, 256, (size_t)(C + Cr) * 4, st>>>(partial, nchunk, HW, C, w1, w2, Cr, plus_one, scale);
+    // work buffers behind the partial sums: mean [N][C], hidden [N][Cr]
+    float *mean = partial + (int64_t)N * nchunk * C;
+    float *hid = mean + (int64_t)N * C;
+    se_mean_kernel<<<(unsigned)(((int64_t)N * C + 255) / 256), 256, 0, st>>>(partial, nchunk, HW, N, C, mean);
+    RGBD_LAUNCH_CHECK();
+    se_hidden_kernel<<<(unsigned)(((int64_t)N * Cr * 32 + 255) / 256), 256, 0, st>>>(mean, w1, N, C, Cr, hid);
+    RGBD_LAUNCH_CHECK();
+    se_gate_kernel<<<(unsigned)(((int64_t)N * C * 32 + 255) / 256), 256, 0, st>>>(hid, w2, N, C, Cr, plus_one, scale);
     RGBD_LAUNCH_CHECK();
     return RGBD_OK;
 }
@@ -210,16 +241,16 @@ extern "C" int rgbd_maxpool7s3(const void *x, void *y, int32_t dtype, int32_t N,
 }
 
 extern "C" int rgbd_nchw_to_nhwc(const float *x, void *y, int32_t dtype, int32_t N, int32_t C, int32_t H,
-                                 int32_t W, int32_t y_cstride, int32_t y_coff, void *stream) {
+                                 int32_t W, int32_t y_cstride, int32_t y_coff, int32_t split3, void *stream) {
     RGBD_CHECK_ARG(x && y, "null pointer");
     RGBD_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0, "dims");
     const int grid = rgbd_grid_for((int64_t)N * C * H * W, 256);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == RGBD_DT_F32)
-        nchw_to_nhwc_kernel<float><<<grid, 256, 0, st>>>(x, (float *)y, N, C, H, W, y_cstride, y_coff);
+        nchw_to_nhwc_kernel<float><<<grid, 256, 0, st>>>(x, (float *)y, N, C, H, W, y_cstride, y_coff, split3);
     else
         nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, (__nv_bfloat16 *)y, N, C, H, W, y_cstride,
-                                                                  y_coff);
+                                                                  y_coff, split3);
     RGBD_LAUNCH_CHECK();
     return RGBD_OK;
 }

@@ -160,12 +160,12 @@ class ELIC_united(nn.Module):
     def act_dtype(self):
         return torch.float32 if self.precision == "fp32" else torch.bfloat16
 
-    def _pc(self, mod, in_perm=None):
+    def _pc(self, mod, in_perm=None, split3=False):
         if self._packed is None:
             self._packed = {}
-        key = id(mod)
+        key = (id(mod), split3)
         if key not in self._packed:
-            self._packed[key] = PackedConv(mod, self.device, in_perm)
+            self._packed[key] = PackedConv(mod, self.device, in_perm, split3)
         return self._packed[key]
 
     def _dev32(self, key, make):
@@ -272,7 +272,7 @@ class ELIC_united(nn.Module):
 
             def step(mod, x, is_rgb):
                 if isinstance(mod, (nn.Conv2d, nn.ConvTranspose2d)):
-                    pc = self._pc(mod)
+                    pc = self._pc(mod, split3=(x.C == 3 * mod.in_channels))
                     Ho, Wo, _ = pc.launches(x.H, x.W)
                     return b.conv(pc, x, out=out_for(is_rgb, Ho, Wo, pc.Cout),
                                   out_dtype=final_dtype if last else None)
@@ -468,13 +468,16 @@ class ELIC_united(nn.Module):
     def _common_front(self, b, B, H, W):
         """image -> g_a -> h_a. Returns io views."""
         p = b.prog
-        x_r = b.alloc(B, H, W, 3)
-        x_d = b.alloc(B, H, W, 1)
+        # bf16 tensor-core mode: the images enter as a two-term bf16 expansion [hi | lo | hi] so the first
+        # layer keeps fp32-like accuracy (16-bit depth is represented exactly) at no extra MMA cost
+        split = 1 if b.tensor_cores else 0
+        x_r = b.alloc(B, H, W, 9 if split else 3)
+        x_d = b.alloc(B, H, W, 3 if split else 1)
         in_r = b.raw((B, 3, H, W), torch.float32)
         in_d = b.raw((B, 1, H, W), torch.float32)
         p.io["rgb"], p.io["depth"] = in_r, in_d
-        b.op("rgbd_nchw_to_nhwc", in_r.data_ptr(), x_r.ptr(), _DT[x_r.dtype], B, 3, H, W, x_r.cstride, x_r.coff)
-        b.op("rgbd_nchw_to_nhwc", in_d.data_ptr(), x_d.ptr(), _DT[x_d.dtype], B, 1, H, W, x_d.cstride, x_d.coff)
+        b.op("rgbd_nchw_to_nhwc", in_r.data_ptr(), x_r.ptr(), _DT[x_r.dtype], B, 3, H, W, x_r.cstride, x_r.coff, split)
+        b.op("rgbd_nchw_to_nhwc", in_d.data_ptr(), x_d.ptr(), _DT[x_d.dtype], B, 1, H, W, x_d.cstride, x_d.coff, split)
         y_r, y_d = self._transform(b, self.g_a.rgb_analysis_transform, self.g_a.depth_analysis_transform,
                                    x_r, x_d, final_dtype=torch.float32)
         z_r, z_d = self._h_a(b, y_r, y_d)

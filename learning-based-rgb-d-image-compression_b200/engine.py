@@ -49,7 +49,7 @@ class PackedConv:
     reference's torch.cat order).
     """
 
-    def __init__(self, mod, device, in_perm=None):
+    def __init__(self, mod, device, in_perm=None, split3=False):
         w = mod.weight.detach().to(device=device, dtype=torch.float32)
         self.transposed = isinstance(mod, torch.nn.ConvTranspose2d)
         if self.transposed:
@@ -66,6 +66,13 @@ class PackedConv:
         taps = taps.reshape(kh * kw, cin, cout)
         if in_perm is not None:
             taps = taps[:, in_perm.to(device), :]
+        self.flop_cin = cin
+        if split3:
+            # two-term bf16 expansion of the weights against an input stored as [hi | lo | hi]:
+            # x*w ~= hi*w_hi + lo*w_hi + hi*w_lo  (see rgbd_nchw_to_nhwc split3)
+            hi = taps.to(torch.bfloat16).to(torch.float32)
+            taps = torch.cat([hi, hi, taps - hi], dim=1)
+            cin = self.Cin = 3 * cin
         self.cout_pad = (cout + 15) // 16 * 16
         packed = torch.zeros(kh * kw, cin, self.cout_pad, device=device, dtype=torch.float32)
         packed[:, :, :cout] = taps
@@ -210,8 +217,9 @@ class Builder:
         if out is None:
             out = self.alloc(x.N, Ho, Wo, pc.Cout, out_dtype)
         assert (out.N, out.H, out.W, out.C) == (x.N, Ho, Wo, pc.Cout), ((out.N, out.H, out.W, out.C), (x.N, Ho, Wo, pc.Cout))
-        use_tc = (self.tensor_cores and x.dtype == torch.bfloat16 and x.cstride % 8 == 0 and x.coff % 8 == 0
-                  and pc.Cin >= 16)
+        # small Cin (the 3 / 1-channel image layers) still goes to the tensor cores: TMA zero-fills the
+        # channel block beyond Cin, so a tap costs one K=16 MMA
+        use_tc = self.tensor_cores and x.dtype == torch.bfloat16 and x.cstride % 8 == 0 and x.coff % 8 == 0
         scaled = None
         if use_tc and in_scale is not None:
             # the TMA-fed A operand never passes through registers: apply the SE gate in a separate pass
@@ -267,7 +275,7 @@ class Builder:
             run.is_tc = use_tc
             kind = ("deconv" if pc.transposed else "conv") + f"{pc.k}x{pc.k}" + (f"s{pc.stride}" if pc.stride > 1 else "")
             run.label = f"{'tc' if use_tc else 'simt'} {kind} {pc.Cin}->{pc.Cout} @{ln['Hs']}x{ln['Ws']}"
-            run.flops = 2 * x.N * ln["Hs"] * ln["Ws"] * len(ln["taps"]) * pc.Cin * pc.Cout
+            run.flops = 2 * x.N * ln["Hs"] * ln["Ws"] * len(ln["taps"]) * pc.flop_cin * pc.Cout
             self.prog.flops += run.flops
         self.prog.keep.extend([pc, x.buf, out.buf])
         if scaled is not None:
@@ -279,7 +287,7 @@ class Builder:
         Cr = w1.shape[0]
         HW = x.H * x.W
         nchunk = max(1, min(64, HW // 64))
-        partial = self.raw((x.N, nchunk, x.C), torch.float32)
+        partial = self.raw((x.N * (nchunk * x.C + x.C + Cr),), torch.float32)
         scale = self.raw((x.N, x.C), torch.float32)
         self.op("rgbd_se_scale", x.ptr(), _DT[x.dtype], x.N, HW, x.C, x.cstride, x.coff, w1.data_ptr(),
                 w2.data_ptr(), Cr, int(plus_one), partial.data_ptr(), nchunk, scale.data_ptr())

@@ -58,7 +58,7 @@ _PROTOS = {
     "rgbd_conv_tc_run": [_vp, _vp],
     "rgbd_se_scale": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp],
     "rgbd_maxpool7s3": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
-    "rgbd_nchw_to_nhwc": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "rgbd_nchw_to_nhwc": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_nhwc_to_nchw": [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_scale_channels": [_vp, _vp, _i32, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_copy_view": [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp],

@@ -222,7 +222,7 @@ def test_se_maxpool_layout():
     img = torch.rand(2, 3, 16, 20) * 1.4 - 0.2
     nhwc = torch.zeros(2, 16, 20, 3, device=DEV)
     back = torch.zeros(2, 3, 16, 20, device=DEV)
-    L.call("rgbd_nchw_to_nhwc", img.to(DEV).data_ptr(), nhwc.data_ptr(), L.DT_F32, 2, 3, 16, 20, 3, 0, sp())
+    L.call("rgbd_nchw_to_nhwc", img.to(DEV).data_ptr(), nhwc.data_ptr(), L.DT_F32, 2, 3, 16, 20, 3, 0, 0, sp())
     L.call("rgbd_nhwc_to_nchw", nhwc.data_ptr(), L.DT_F32, back.data_ptr(), 2, 3, 16, 20, 3, 0, 1, sp())
     assert torch.equal(nhwc.cpu(), img.permute(0, 2, 3, 1))
     assert torch.equal(back.cpu(), img.clamp(0, 1))
@@ -307,6 +307,8 @@ def bf16_ref(mod, x):
 
 
 TC_CONVS = [
+    ("5x5s2_rgb_3_192", lambda: nn.Conv2d(3, 192, 5, 2, 2), (2, 3, 64, 80)),
+    ("5x5s2_depth_1_192", lambda: nn.Conv2d(1, 192, 5, 2, 2), (1, 1, 64, 64)),
     ("1x1_192_96", lambda: nn.Conv2d(192, 96, 1), (2, 192, 32, 40)),
     ("3x3_96_96_ragged", lambda: nn.Conv2d(96, 96, 3, 1, 1), (2, 96, 19, 21)),
     ("5x5s2_384_192", lambda: nn.Conv2d(384, 192, 5, 2, 2), (1, 384, 32, 48)),
@@ -374,3 +376,26 @@ def test_conv_tc_is_deterministic_and_batch_invariant():
     for i in range(3):
         one = run_conv_tc(mod, x[i:i + 1], out_dtype=torch.float32)
         assert torch.equal(one[0], full[i])
+
+
+def test_split_bf16_first_layer_is_fp32_accurate():
+    """Image layers on the tensor cores: [hi | lo | hi] input x [w_hi | w_hi | w_lo] weights keeps the
+    16-bit depth exact and the product accurate to ~2^-16 (vs 2^-9 for plain bf16)."""
+    from rgbd_b200 import lib as L
+    from rgbd_b200.engine import Builder, PackedConv, View
+    torch.manual_seed(21)
+    for cin in (3, 1):
+        mod = nn.Conv2d(cin, 192, 5, 2, 2).eval()
+        img = torch.round(torch.rand(2, cin, 64, 96) * 65535) / 65535
+        b = Builder(torch.device(DEV), torch.bfloat16, tensor_cores=True)
+        x = b.alloc(2, 64, 96, 3 * cin)
+        src = img.to(DEV)
+        b.op("rgbd_nchw_to_nhwc", src.data_ptr(), x.ptr(), L.DT_BF16, 2, cin, 64, 96, x.cstride, x.coff, 1)
+        out = b.conv(PackedConv(mod, torch.device(DEV), split3=True), x, out_dtype=torch.float32)
+        assert b.prog.n_tc == 1
+        b.prog.run()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            want = mod(img)
+        got = out.torch().float().cpu().permute(0, 3, 1, 2)
+        assert rel_err(got, want) < 5e-5, (cin, rel_err(got, want))
