@@ -14,8 +14,8 @@
 //   * Epilogue warps read the accumulator with tcgen05.ld (one pixel row per thread) and apply
 //     bias / activation / residual / sigmoid-gate / bilinear-add before storing NHWC.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).  Two CTAs fit per SM so one CTA's
-// epilogue overlaps the other's main loop.
+// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).  The kernel is persistent: 2 CTAs per
+// SM walk the tile list; residual / gate operands are prefetched before the accumulator is ready.
 //
 // The K reduction order (tap-major, then channel blocks, fixed MMA order) does not depend on the
 // batch size or on the tile a pixel falls in: encoder and decoder reproduce the same bits.
@@ -25,19 +25,25 @@
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = 64 + 32 * kEpiWarps;     // TMA warp + MMA warp + epilogue warps
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 B = one swizzle row
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB
-constexpr int kSmemBudget = 110 * 1024;           // per CTA, so that two CTAs share an SM
+// two persistent CTAs per SM (two TMA / MMA issuers and two epilogues in flight); the budget leaves
+// room for one rANS decode block (~56 KB) on the same SM
+constexpr int kSmemBudget = 84 * 1024;
 constexpr int kMaxStages = 6;
+constexpr uint32_t kTmemCols = 256;               // per CTA: two accumulator buffers when BN <= 128, else one
+constexpr int kMaxChunks = 16;                    // 16-column chunks per tile (BN / 16)
+constexpr int kPrefetch = 4;                      // residual / gate chunks requested ahead of use
 
 struct TcParams {
     CUtensorMap amap[4];
     CUtensorMap bmap;
     rgbd_conv_desc d;
     int32_t TW, TH, tiles_x, tiles_y;
-    int32_t BN, kblocks, stages, tmem_cols;
+    int32_t BN, kblocks, stages, n_ntiles, total_tiles, acc_bufs;
     int8_t tap_map[RGBD_MAX_TAPS], qy[RGBD_MAX_TAPS], qx[RGBD_MAX_TAPS];
     int8_t _pad[5];
 };
@@ -47,6 +53,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -205,9 +214,42 @@ template <> __device__ __forceinline__ void store16<float>(float *p, bool vec, i
     }
 }
 
-template <typename TOut>
+__device__ __forceinline__ void unpack8(const uint4 &q, float *v) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w[i]);
+        v[2 * i] = __low2float(h);
+        v[2 * i + 1] = __high2float(h);
+    }
+}
+
+struct TileCoord {
+    int n, oy0, ox0, co0, bn;
+};
+__device__ __forceinline__ TileCoord tile_coord(const TcParams &p, int tile) {
+    // n-tile fastest: CTAs that run side by side share the same A tile through L2
+    TileCoord t;
+    const int nt = tile % p.n_ntiles;
+    const int mt = tile / p.n_ntiles;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    t.n = mt / tiles_per_img;
+    const int trem = mt - t.n * tiles_per_img;
+    t.oy0 = (trem / p.tiles_x) * p.TH;
+    t.ox0 = (trem % p.tiles_x) * p.TW;
+    t.co0 = nt * p.BN;
+    t.bn = min(p.BN, p.d.cout_pad - t.co0);   // multiple of 16
+    return t;
+}
+
+// Persistent kernel: two CTAs per SM loop over output tiles (tile = blockIdx.x + i * gridDim.x).
+// The smem ring and its mbarrier phases run continuously across tiles; when the N tile is <= 128
+// columns the accumulator is double buffered in the CTA's 256 TMEM columns so that the epilogue of
+// tile i overlaps the MMAs of tile i + 1 (wider tiles rely on the sibling CTA for overlap).
+template <typename TOut, int kEpi>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_tc_kernel(const __grid_constant__ TcParams p) {
+    constexpr bool kGate = kEpi == RGBD_EPI_GATE;
     extern __shared__ uint8_t smem_raw[];
     using bf16 = __nv_bfloat16;
     const rgbd_conv_desc &d = p.d;
@@ -219,8 +261,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxStages);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -229,70 +272,76 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar(a), 1);
+            mbar_init(tmem_empty_bar(a), kEpiWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-
-    // tile coordinates
-    const int tiles_per_img = p.tiles_x * p.tiles_y;
-    const int n = blockIdx.x / tiles_per_img;
-    const int trem = blockIdx.x - n * tiles_per_img;
-    const int oy0 = (trem / p.tiles_x) * p.TH;
-    const int ox0 = (trem % p.tiles_x) * p.TW;
-    const int co0 = blockIdx.y * p.BN;
-    const int bn = min(p.BN, d.cout_pad - co0);   // multiple of 16
     const int num_it = d.ntaps * p.kblocks;
 
     if (warp == 0) {
+        // =========================== TMA producer ===========================
         if (lane == 0) {
-            for (int it = 0; it < num_it; ++it) {
-                const int t = it / p.kblocks, kb = it - t * p.kblocks;
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                const uint32_t sa = base + (uint32_t)s * stage_bytes;
-                mbar_expect_tx(full_bar(s), (uint32_t)kABytes + b_bytes);   // TMA delivers full boxes (OOB zero-filled)
-                tma_load_4d(sa, &p.amap[p.tap_map[t]], full_bar(s), kb * kBlockK, ox0 + p.qx[t], oy0 + p.qy[t], n);
-                tma_load_3d(sa + kABytes, &p.bmap, full_bar(s), kb * kBlockK, co0, d.wtap[t]);
+            uint32_t g = 0;   // running k-iteration count across tiles
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord(p, tile);
+                for (int it = 0; it < num_it; ++it, ++g) {
+                    const int t = it / p.kblocks, kb = it - t * p.kblocks;
+                    const int s = (int)(g % (uint32_t)p.stages);
+                    const uint32_t ph = (g / (uint32_t)p.stages) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sa = base + (uint32_t)s * stage_bytes;
+                    mbar_expect_tx(full_bar(s), (uint32_t)kABytes + b_bytes);   // TMA delivers full boxes
+                    tma_load_4d(sa, &p.amap[p.tap_map[t]], full_bar(s), kb * kBlockK, tc.ox0 + p.qx[t],
+                                tc.oy0 + p.qy[t], tc.n);
+                    tma_load_3d(sa + kABytes, &p.bmap, full_bar(s), kb * kBlockK, tc.co0, d.wtap[t]);
+                }
             }
         }
     } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(kTileM, bn);
-            for (int it = 0; it < num_it; ++it) {
-                const int t = it / p.kblocks, kb = it - t * p.kblocks;
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                mbar_wait(full_bar(s), ph);
+            uint32_t g = 0;
+            int li = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+                const TileCoord tc = tile_coord(p, tile);
+                const int acc = li % p.acc_bufs;
+                const uint32_t use = (uint32_t)(li / p.acc_bufs);
+                mbar_wait(tmem_empty_bar(acc), (use & 1u) ^ 1u);   // epilogue drained this buffer
                 tc_fence_after();
-                const uint32_t sa = base + (uint32_t)s * stage_bytes;
-                const uint64_t adesc = make_smem_desc(sa);
-                const uint64_t bdesc = make_smem_desc(sa + kABytes);
-                // only the 16-channel groups that hold real input channels (tail block may be short)
-                const int kleft = d.Cin - kb * kBlockK;
-                const int nk = kleft >= kBlockK ? 4 : (kleft + 15) >> 4;
-                for (int k = 0; k < nk; ++k)
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                              (it > 0 || k > 0) ? 1u : 0u);
-                umma_commit(empty_bar(s));   // frees the smem stage once these MMAs have read it
-                (void)t;
+                const uint32_t idesc = make_idesc(kTileM, tc.bn);
+                const uint32_t dcol = tmem_base + (uint32_t)acc * 128u;
+                for (int it = 0; it < num_it; ++it, ++g) {
+                    const int kb = it % p.kblocks;
+                    const int s = (int)(g % (uint32_t)p.stages);
+                    const uint32_t ph = (g / (uint32_t)p.stages) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + (uint32_t)s * stage_bytes;
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t bdesc = make_smem_desc(sa + kABytes);
+                    // only the 16-channel groups that hold real input channels (tail block may be short)
+                    const int kleft = d.Cin - kb * kBlockK;
+                    const int nk = kleft >= kBlockK ? 4 : (kleft + 15) >> 4;
+                    for (int k = 0; k < nk; ++k)
+                        umma_bf16(dcol, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                  (it > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(empty_bar(s));   // frees the smem stage once these MMAs have read it
+                }
+                umma_commit(tmem_full_bar(acc));
             }
-            umma_commit(tmem_full_bar);
         }
     } else {
-        // ---------------- epilogue: TMEM -> registers -> NHWC global ----------------
+        // ============ epilogue: TMEM -> registers -> NHWC global (8 warps) ============
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;          // pixel index inside the tile
         const int th = row / p.TW, tw = row - th * p.TW;
-        const int sy = oy0 + th, sx = ox0 + tw;    // site in the Hs x Ws output lattice
-        const bool valid = sy < d.Hs && sx < d.Ws;
-        const int oy = sy * d.o_step + d.o_off_y, ox = sx * d.o_step + d.o_off_x;
-        const int64_t opix = ((int64_t)n * d.Ho + oy) * d.Wo + ox;
         TOut *y = reinterpret_cast<TOut *>(d.y);
         TOut *y2 = reinterpret_cast<TOut *>(d.y2);
         const bf16 *res = reinterpret_cast<const bf16 *>(d.res);
@@ -302,68 +351,127 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         const bool y2_vec = ((d.y2_cstride | d.y2_coff) % kVecOut) == 0;
         const bool res_vec = ((d.res_cstride | d.res_coff) & 7) == 0;
         const bool mul_vec = ((d.mul_cstride | d.mul_coff) & 7) == 0;
-        int by0 = 0, by1 = 0, bx0 = 0, bx1 = 0;
-        float ly = 0.f, lx = 0.f;
-        if (d.epi == RGBD_EPI_BILERP && valid) {
-            bilerp_axis(oy, d.res_H, d.Ho, by0, by1, ly);
-            bilerp_axis(ox, d.res_W, d.Wo, bx0, bx1, lx);
-        }
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        for (int c = 0; c < bn; c += 16) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
-            const int co = co0 + c;
-            const int nvalid = d.Cout - co;
-            if (!valid || nvalid <= 0) continue;
-            if (d.bias) {
+        const bool res_direct = res != nullptr && kEpi != RGBD_EPI_BILERP;
+        int li = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+            const TileCoord tc = tile_coord(p, tile);
+            const int acc = li % p.acc_bufs;
+            const uint32_t use = (uint32_t)(li / p.acc_bufs);
+            const int sy = tc.oy0 + th, sx = tc.ox0 + tw;    // site in the Hs x Ws output lattice
+            const bool valid = sy < d.Hs && sx < d.Ws;
+            const int oy = sy * d.o_step + d.o_off_y, ox = sx * d.o_step + d.o_off_x;
+            const int64_t opix = ((int64_t)tc.n * d.Ho + oy) * d.Wo + ox;
+            const int c_begin = 0;
+            const int c_end = tc.bn >> 4;
+            // residual / gate operands of this thread's pixel are requested BEFORE the accumulator is
+            // ready, so their HBM latency hides behind the MMAs
+            uint4 pr[2 * kPrefetch];
+            uint4 pm[kGate ? 2 * kPrefetch : 1];
+            auto prefetch = [&](int k, int slot) {
+                const int c = c_begin + k;
+                const int co = tc.co0 + c * 16;
+                const bool on = valid && c < c_end && d.Cout - co >= 16;
+                pr[2 * slot] = pr[2 * slot + 1] = make_uint4(0, 0, 0, 0);
+                if (on && res_direct && res_vec) {
+                    const uint4 *q = reinterpret_cast<const uint4 *>(res + opix * d.res_cstride + d.res_coff + co);
+                    pr[2 * slot] = q[0];
+                    pr[2 * slot + 1] = q[1];
+                }
+                if (kGate) {
+                    pm[2 * slot] = pm[2 * slot + 1] = make_uint4(0, 0, 0, 0);
+                    if (on && mul_vec) {
+                        const uint4 *q = reinterpret_cast<const uint4 *>(mul + opix * d.mul_cstride + d.mul_coff + co);
+                        pm[2 * slot] = q[0];
+                        pm[2 * slot + 1] = q[1];
+                    }
+                }
+            };
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += (i < nvalid) ? __ldg(d.bias + co + i) : 0.f;
+            for (int k = 0; k < kPrefetch; ++k) prefetch(k, k);
+            int by0 = 0, by1 = 0, bx0 = 0, bx1 = 0;
+            float ly = 0.f, lx = 0.f;
+            if (kEpi == RGBD_EPI_BILERP && valid) {
+                bilerp_axis(oy, d.res_H, d.Ho, by0, by1, ly);
+                bilerp_axis(ox, d.res_W, d.Wo, bx0, bx1, lx);
             }
-            if (d.epi == RGBD_EPI_LINEAR) {
-                if (res) {
-                    float r[16];
-                    load16<bf16>(res + opix * d.res_cstride + d.res_coff + co, res_vec, nvalid, r);
+            mbar_wait(tmem_full_bar(acc), use & 1u);
+            tc_fence_after();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += r[i];
+            for (int k = 0; k < kMaxChunks; ++k) {
+                const int c = c_begin + k;
+                if (c < c_end) {            // warp-uniform
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 128 + c * 16), v);
+                const int co = tc.co0 + c * 16;
+                const int nvalid = d.Cout - co;
+                if (valid && nvalid > 0) {
+                const bool full16 = nvalid >= 16;
+                if (d.bias) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += (i < nvalid) ? __ldg(d.bias + co + i) : 0.f;
                 }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = act_fn(v[i], d.act);
-            } else if (d.epi == RGBD_EPI_GATE) {
-                float m[16];
-                load16<bf16>(mul + opix * d.mul_cstride + d.mul_coff + co, mul_vec, nvalid, m);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = m[i] * (1.0f / (1.0f + __expf(-v[i])));
-                if (res) {
-                    float r[16];
-                    load16<bf16>(res + opix * d.res_cstride + d.res_coff + co, res_vec, nvalid, r);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += r[i];
+                float r[16];
+                if (res_direct) {
+                    if (res_vec && full16) {
+                        unpack8(pr[2 * (k % kPrefetch)], r);
+                        unpack8(pr[2 * (k % kPrefetch) + 1], r + 8);
+                    } else {
+                        load16<bf16>(res + opix * d.res_cstride + d.res_coff + co, false, nvalid, r);
+                    }
                 }
-            } else {  // RGBD_EPI_BILERP
-                const int64_t rb = (int64_t)n * d.res_H * d.res_W;
-                const int cc = d.res_coff + co;
-                float a00[16], a01[16], a10[16], a11[16];
-                load16<bf16>(res + (rb + (int64_t)by0 * d.res_W + bx0) * d.res_cstride + cc, res_vec, nvalid, a00);
-                load16<bf16>(res + (rb + (int64_t)by0 * d.res_W + bx1) * d.res_cstride + cc, res_vec, nvalid, a01);
-                load16<bf16>(res + (rb + (int64_t)by1 * d.res_W + bx0) * d.res_cstride + cc, res_vec, nvalid, a10);
-                load16<bf16>(res + (rb + (int64_t)by1 * d.res_W + bx1) * d.res_cstride + cc, res_vec, nvalid, a11);
+                if (kGate) {
+                    float m[16];
+                    if (mul_vec && full16) {
+                        unpack8(pm[2 * (k % kPrefetch)], m);
+                        unpack8(pm[2 * (k % kPrefetch) + 1], m + 8);
+                    } else {
+                        load16<bf16>(mul + opix * d.mul_cstride + d.mul_coff + co, false, nvalid, m);
+                    }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float up = (1.f - ly) * ((1.f - lx) * a00[i] + lx * a01[i]) +
-                                     ly * ((1.f - lx) * a10[i] + lx * a11[i]);
-                    v[i] = act_fn(v[i] + up, d.act);
+                    for (int i = 0; i < 16; ++i) v[i] = m[i] * (1.0f / (1.0f + __expf(-v[i])));
+                    if (res_direct) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += r[i];
+                    }
+                } else if (kEpi == RGBD_EPI_LINEAR) {
+                    if (res_direct) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += r[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = act_fn(v[i], d.act);
+                } else {  // RGBD_EPI_BILERP
+                    const int64_t rb = (int64_t)tc.n * d.res_H * d.res_W;
+                    const int cc = d.res_coff + co;
+                    float a00[16], a01[16], a10[16], a11[16];
+                    load16<bf16>(res + (rb + (int64_t)by0 * d.res_W + bx0) * d.res_cstride + cc, res_vec, nvalid, a00);
+                    load16<bf16>(res + (rb + (int64_t)by0 * d.res_W + bx1) * d.res_cstride + cc, res_vec, nvalid, a01);
+                    load16<bf16>(res + (rb + (int64_t)by1 * d.res_W + bx0) * d.res_cstride + cc, res_vec, nvalid, a10);
+                    load16<bf16>(res + (rb + (int64_t)by1 * d.res_W + bx1) * d.res_cstride + cc, res_vec, nvalid, a11);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float up = (1.f - ly) * ((1.f - lx) * a00[i] + lx * a01[i]) +
+                                         ly * ((1.f - lx) * a10[i] + lx * a11[i]);
+                        v[i] = act_fn(v[i] + up, d.act);
+                    }
+                }
+                store16<TOut>(y + opix * d.y_cstride + d.y_coff + co, y_vec, nvalid, v);
+                if (y2) store16<TOut>(y2 + opix * d.y2_cstride + d.y2_coff + co, y2_vec, nvalid, v);
+                }
+                if (k + kPrefetch < kMaxChunks) prefetch(k + kPrefetch, k % kPrefetch);   // refill the slot
                 }
             }
-            store16<TOut>(y + opix * d.y_cstride + d.y_coff + co, y_vec, nvalid, v);
-            if (y2) store16<TOut>(y2 + opix * d.y2_cstride + d.y2_coff + co, y2_vec, nvalid, v);
+            // all of this warp's tcgen05.ld have completed (wait::ld inside tmem_ld16): hand the buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -413,6 +521,7 @@ struct rgbd_conv_tc_plan {
     dim3 grid;
     size_t smem;
     int out_f32;
+    int epi;
 };
 
 extern "C" int rgbd_conv_validate(const rgbd_conv_desc *d);
@@ -457,11 +566,22 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     p.stages = kSmemBudget / stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     if (p.stages < 2) p.stages = 2;
-    p.tmem_cols = 32;
-    while (p.tmem_cols < p.BN) p.tmem_cols *= 2;
-    pl->smem = (size_t)p.stages * stage_bytes + 1024 /*align*/ + 8 * (2 * kMaxStages + 2);
-    pl->grid = dim3((unsigned)((long)d->N * p.tiles_x * p.tiles_y), (unsigned)((d->cout_pad + p.BN - 1) / p.BN));
+    p.acc_bufs = p.BN <= 128 ? 2 : 1;
+    p.n_ntiles = (d->cout_pad + p.BN - 1) / p.BN;
+    const long total = (long)d->N * p.tiles_x * p.tiles_y * p.n_ntiles;
+    RGBD_CHECK_ARG(total < 2147483647L, "too many tiles");
+    p.total_tiles = (int)total;
+    pl->smem = (size_t)p.stages * stage_bytes + 1024 /*align*/ + 8 * (2 * kMaxStages + 6);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
+            num_sms = 148;
+    }
+    pl->grid = dim3((unsigned)(p.total_tiles < 2 * num_sms ? p.total_tiles : 2 * num_sms));
     pl->out_f32 = d->y_dtype == RGBD_DT_F32;
+    pl->epi = d->epi;
 
     // A tensor maps: one per input parity class (i_step == 2) or a single one
     const int st = d->i_step;
@@ -511,8 +631,13 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     }
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        const int cap = 100 * 1024;
+        cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(conv_tc_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(conv_tc_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(conv_tc_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         configured = true;
     }
     *out = pl;
@@ -522,10 +647,17 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
 extern "C" int rgbd_conv_tc_run(const rgbd_conv_tc_plan *pl, void *stream) {
     RGBD_CHECK_ARG(pl != nullptr, "null plan");
     cudaStream_t st = (cudaStream_t)stream;
-    if (pl->out_f32)
-        conv_tc_kernel<float><<<pl->grid, kThreads, pl->smem, st>>>(pl->p);
-    else
-        conv_tc_kernel<__nv_bfloat16><<<pl->grid, kThreads, pl->smem, st>>>(pl->p);
+#define RGBD_TC_LAUNCH(T, E) conv_tc_kernel<T, E><<<pl->grid, kThreads, pl->smem, st>>>(pl->p)
+    if (pl->out_f32) {
+        if (pl->epi == RGBD_EPI_GATE) RGBD_TC_LAUNCH(float, 1);
+        else if (pl->epi == RGBD_EPI_BILERP) RGBD_TC_LAUNCH(float, 2);
+        else RGBD_TC_LAUNCH(float, 0);
+    } else {
+        if (pl->epi == RGBD_EPI_GATE) RGBD_TC_LAUNCH(__nv_bfloat16, 1);
+        else if (pl->epi == RGBD_EPI_BILERP) RGBD_TC_LAUNCH(__nv_bfloat16, 2);
+        else RGBD_TC_LAUNCH(__nv_bfloat16, 0);
+    }
+#undef RGBD_TC_LAUNCH
     RGBD_LAUNCH_CHECK();
     return RGBD_OK;
 }
