@@ -34,8 +34,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU per step (default: by precision)")
-    ap.add_argument("--precision", default=os.environ.get("RGBD_PRECISION", "fp32"), choices=["fp32", "bf16"])
-    ap.add_argument("--slots", type=int, default=3, help="batches in flight per GPU (own program + CUDA stream each)")
+    ap.add_argument("--precision", default=os.environ.get("RGBD_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--slots", type=int, default=6, help="batches in flight per GPU (own program + CUDA stream each)")
     ap.add_argument("--preset", default="realistic")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
@@ -172,7 +172,7 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch or (4 if args.precision == "fp32" else 16)
+    B = args.batch or (2 if args.precision == "fp32" else 16)
 
     net = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4, precision=args.precision).eval()
     net.load_state_dict(rgbd_b200.synthetic.synthetic_state_dict(net, 0, args.preset))
@@ -324,7 +324,7 @@ def conv_roofline(net, B, Hp, Wp, dev):
             total_flops += prog.flops
             n += len(evs)
     return {"tflops": total_flops / (total_ms / 1e3) / 1e12, "ms": total_ms, "launches": n,
-            "kernel": "conv_simt_kernel" if net.precision == "fp32" else "conv (tc + simt)"}
+            "kernel": "conv_simt_kernel" if net.precision == "fp32" else "conv_tc_kernel (tcgen05 implicit GEMM; + conv_simt for the fp32-input h_a layer)"}
 
 
 if __name__ == "__main__":

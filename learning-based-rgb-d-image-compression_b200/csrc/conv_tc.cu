@@ -36,7 +36,8 @@ constexpr int kSmemBudget = 84 * 1024;
 constexpr int kMaxStages = 6;
 constexpr uint32_t kTmemCols = 256;               // per CTA: two accumulator buffers when BN <= 128, else one
 constexpr int kMaxChunks = 16;                    // 16-column chunks per tile (BN / 16)
-constexpr int kPrefetch = 4;                      // residual / gate chunks requested ahead of use
+constexpr int kPrefetchLinear = 4;                // residual chunks requested ahead of use
+constexpr int kPrefetchGate = 4;                  // residual + gate chunks (twice the registers)
 
 struct TcParams {
     CUtensorMap amap[4];
@@ -250,6 +251,7 @@ template <typename TOut, int kEpi>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_tc_kernel(const __grid_constant__ TcParams p) {
     constexpr bool kGate = kEpi == RGBD_EPI_GATE;
+    constexpr int kPrefetch = kGate ? kPrefetchGate : kPrefetchLinear;
     extern __shared__ uint8_t smem_raw[];
     using bf16 = __nv_bfloat16;
     const rgbd_conv_desc &d = p.d;
@@ -428,7 +430,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                         load16<bf16>(mul + opix * d.mul_cstride + d.mul_coff + co, false, nvalid, m);
                     }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = m[i] * (1.0f / (1.0f + __expf(-v[i])));
+                    for (int i = 0; i < 16; ++i) v[i] = m[i] * __fdividef(1.0f, 1.0f + __expf(-v[i]));
                     if (res_direct) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] += r[i];
