@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU per step (default: by precision)")
     ap.add_argument("--precision", default=os.environ.get("RGBD_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--slots", type=int, default=6, help="batches in flight per GPU (own program + CUDA stream each)")
+    ap.add_argument("--graphs", type=int, default=0, help="replay each slot's launch list as a CUDA graph")
     ap.add_argument("--preset", default="realistic")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
@@ -178,6 +179,7 @@ def run_b200(args):
     net.load_state_dict(rgbd_b200.synthetic.synthetic_state_dict(net, 0, args.preset))
     net.update(force=True)
     net = net.to(dev)
+    net.use_cuda_graph = bool(args.graphs)
     # each rank owns its contiguous shard of the global batch (weak scaling: S x B pairs per GPU and
     # step); S batches are in flight on S CUDA streams so that the serial rANS kernels of one batch
     # overlap the convolutions of the others
@@ -280,10 +282,10 @@ def run_b200(args):
             "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": f"ELIC_united compress+decompress, {world}x{S}x{B} pairs/step of "
                                    f"{args.height}x{args.width} (padded {Hp}x{Wp}), preset {args.preset}, "
-                                   f"weights calibrated random-init", "pairs_per_gpu": S * B, "batch": B, "slots_in_flight": S, "precision": args.precision,
+                                   f"weights calibrated random-init", "pairs_per_gpu": S * B, "batch": B, "slots_in_flight": S, "precision": args.precision, "cuda_graphs": bool(args.graphs),
                        "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
                        "parallelism": f"dp{world} (images sharded, no data-path collective)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": launches,
             "clocks": clocks,

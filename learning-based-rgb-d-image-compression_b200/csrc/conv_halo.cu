@@ -1,0 +1,1038 @@
+// tcgen05 tensor-core implicit-GEMM convolution, halo-resident form (bf16 operands, fp32 TMEM
+// accumulators).  One persistent CTA per SM.
+//
+// GEMM view: D[pos, co] = sum_{group, kblock, tap in group} A_group,kblock[pos + shift(tap), :] * W[tap][co][kblock]
+//   * A "super-tile" is R rows x P columns of one image's output lattice laid out as R*P <= 256
+//     consecutive *positions* (row pitch P = TW + ext_x - 1: TW useful columns plus the filter's
+//     horizontal extent).  Positions 0..127 and 128..255 are the M = 128 rows of up to two
+//     accumulators (MT = 1 or 2) that share every weight fetch.
+//   * For each (tap group, 64-channel block) ONE 4-D TMA box {64 ch, P, R + ext_y - 1, 1} of the NHWC
+//     input — the tile plus its halo — lands in shared memory as consecutive 128-byte rows with the
+//     128-byte swizzle.  Because the swizzle is a function of the absolute shared-memory address, the
+//     A operand of tap (qy, qx) is the SAME halo tile read through a UMMA descriptor whose start
+//     address is shifted by (qy * P + qx) rows (verified on B200: scratch/desc_test.cu).  A k x k
+//     filter therefore fetches its input once instead of k*k times.  Out-of-image rows/columns are
+//     zero-filled by TMA (= the reference's zero padding).  A tap group is the set of taps that read
+//     the same input lattice: one group for stride 1, the four input parity classes for stride 2
+//     (tensor maps with doubled strides).
+//   * B operand: 3-D TMA box {64 ci, BN co, 1 tap} of the packed bf16 weights [tap][co][ci], in its
+//     own, deeper ring; each B stage feeds the MMAs of both accumulators.
+//   * Residual adds of RGBD_EPI_LINEAR (ResidualBottleneck / ResidualUnit skip connections) ride on
+//     the tensor core: the residual tile is one more A operand multiplied by an identity B tile, so
+//     its HBM latency is hidden by the same TMA pipeline as the activations and the epilogue issues
+//     no global loads at all.
+//   * Warp roles (384 threads): warp 0 = A producer, warp 1 = B producer, warps 2 / 3 = MMA issuers of
+//     accumulator 0 / 1 (warp 2 also owns the TMEM allocation), warps 4..11 = epilogue (TMEM lane quadrant = warp % 4; warps
+//     4..7 drain accumulator 0, warps 8..11 accumulator 1, or the odd column chunks when MT = 1).
+//     TMEM: 512 columns = 2 buffers x 2 accumulators x 128 columns, so the epilogue of super-tile i
+//     overlaps the MMAs of super-tile i + 1.
+//
+// The K reduction order (group, channel block, tap, 16-channel step; residual last) is fixed and does
+// not depend on the batch size or on where a pixel falls inside a tile: encoder and decoder reproduce
+// the same bits.
+#include "common.cuh"
+#include <cuda.h>
+#include <new>
+#include <cstdlib>
+
+namespace {
+
+constexpr int kEpiWarps = 8;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);   // 384
+constexpr int kBlockK = 64;                        // bf16 elements = 128 B = one swizzle row
+constexpr int kMaxA = 4, kMaxB = 8;                // ring depths
+constexpr int kRingBudget = 160 * 1024;            // A ring + B ring; leaves room for a rANS block on the SM
+constexpr int kMaxAStage = 52 * 1024;              // halo tile (one channel block)
+constexpr int kMinSmem = 120 * 1024;               // > half an SM: never two of these CTAs on one SM (512 TMEM columns each)
+constexpr uint32_t kTmemCols = 512;
+constexpr int kMaxGroups = 4;
+constexpr int kMaxBias = 1024;
+
+struct HParams {
+    CUtensorMap amap[4];
+    CUtensorMap bmap, rmap, emap;
+    rgbd_conv_desc d;
+    int32_t TW, R, P, MT, box_rows;
+    int32_t tiles_x, tiles_y, BN, kblocks, n_ntiles, total_tiles;
+    int32_t nA, nB, a_bytes, a_tx, r_tx, b_bytes, tps;   // tps: taps per weight stage (stage = tps * b_bytes)
+    int32_t ngroups, res_blocks;
+    int8_t g_map[kMaxGroups], g_qy[kMaxGroups], g_qx[kMaxGroups], g_first[kMaxGroups + 1];
+    int16_t t_shift[RGBD_MAX_TAPS];
+    int8_t t_w[RGBD_MAX_TAPS];
+    long long *dbg;   // optional cycle counters of CTA 0 (RGBD_TC_TRACE = device pointer to 16 int64), else NULL
+};
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a mis-encoded tensor map would otherwise hang the GPU forever.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s
+            printf("rgbd conv_halo: mbarrier timeout (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
+            __trap();
+        }
+    }
+}
+// wait that adds the stalled cycles to *acc when tracing
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool tr, long long &acc) {
+    if (!tr) {
+        mbar_wait(bar, parity);
+        return;
+    }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns; the caller waits (tmem_ld_wait) before reading v
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// the loaded registers are only defined after the wait: naming them as in/out operands keeps the compiler from
+// scheduling any use of them above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t *r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// the MMAs of one weight stage into one accumulator: nk 16-channel steps (32 B = 2 descriptor units apart)
+__device__ __forceinline__ void issue_mmas(uint32_t dcol, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t started, int nk) {
+    if (nk == 4) {
+        umma_bf16(dcol, adesc, bdesc, idesc, started);
+        umma_bf16(dcol, adesc + 2, bdesc + 2, idesc, 1u);
+        umma_bf16(dcol, adesc + 4, bdesc + 4, idesc, 1u);
+        umma_bf16(dcol, adesc + 6, bdesc + 6, idesc, 1u);
+    } else {
+        for (int k = 0; k < nk; ++k)
+            umma_bf16(dcol, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, started | (uint32_t)k);
+    }
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1),
+//   [32,46) stride byte offset >> 4 (1024 B between 8-row groups), [46,48) version = 1,
+//   [49,52) base offset = 0 (also for row-shifted starts: the swizzle uses absolute address bits),
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format
+// BF16 (bits 7, 10), K-major A and B, N >> 3 at [17,23), M >> 4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+    if (act == RGBD_ACT_RELU) return v > 0.f ? v : 0.f;
+    if (act == RGBD_ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
+    return v;
+}
+__device__ __forceinline__ void bilerp_axis(int dst, int in_size, int out_size, int &i0, int &i1, float &l1) {
+    const float scale = (float)in_size / (float)out_size;
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+}
+
+__device__ __forceinline__ void unpack8(const uint4 &q, float *v) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w[i]);
+        v[2 * i] = __low2float(h);
+        v[2 * i + 1] = __high2float(h);
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float *v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+// 16 consecutive bf16 channels of one pixel -> fp32 (vector path when 16-byte aligned and complete)
+__device__ __forceinline__ void load16_bf16(const __nv_bfloat16 *p, bool vec, int nvalid, float *v) {
+    if (vec && nvalid >= 16) {
+        unpack8(reinterpret_cast<const uint4 *>(p)[0], v);
+        unpack8(reinterpret_cast<const uint4 *>(p)[1], v + 8);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = i < nvalid ? __bfloat162float(p[i]) : 0.f;
+    }
+}
+template <typename T> __device__ __forceinline__ void store16(T *p, bool vec, int nvalid, const float *v);
+template <> __device__ __forceinline__ void store16<__nv_bfloat16>(__nv_bfloat16 *p, bool vec, int nvalid, const float *v) {
+    if (vec && nvalid >= 16) {
+        reinterpret_cast<uint4 *>(p)[0] = pack8(v);
+        reinterpret_cast<uint4 *>(p)[1] = pack8(v + 8);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < nvalid) p[i] = __float2bfloat16_rn(v[i]);
+    }
+}
+template <> __device__ __forceinline__ void store16<float>(float *p, bool vec, int nvalid, const float *v) {
+    if (vec && nvalid >= 16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4 *>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < nvalid) p[i] = v[i];
+    }
+}
+
+// position in a ring of n stages: stage index + phase parity, advanced without integer division
+struct RingPos {
+    int s;
+    uint32_t ph;
+    __device__ __forceinline__ void next(int n) {
+        if (++s == n) {
+            s = 0;
+            ph ^= 1u;
+        }
+    }
+};
+
+struct TileCoord {
+    int n, oy0, ox0, co0, bn;
+};
+__device__ __forceinline__ TileCoord tile_coord(const HParams &p, int tile) {
+    // n-tile fastest: CTAs that run side by side share the same A halo through L2
+    TileCoord t;
+    const int nt = tile % p.n_ntiles;
+    const int mt = tile / p.n_ntiles;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    t.n = mt / tiles_per_img;
+    const int trem = mt - t.n * tiles_per_img;
+    t.oy0 = (trem / p.tiles_x) * p.R;
+    t.ox0 = (trem % p.tiles_x) * p.TW;
+    t.co0 = nt * p.BN;
+    t.bn = min(p.BN, p.d.cout_pad - t.co0);   // multiple of 16
+    return t;
+}
+
+template <typename TOut, int kEpi>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ HParams p) {
+    constexpr bool kGate = kEpi == RGBD_EPI_GATE;
+    extern __shared__ uint8_t smem_raw[];
+    using bf16 = __nv_bfloat16;
+    const rgbd_conv_desc &d = p.d;
+    // 1024-byte aligned carve-up: [A ring | B ring | barriers | tmem ptr | bias]
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t a_base = base;
+    const uint32_t b_base = a_base + (uint32_t)(p.nA * p.a_bytes);
+    const uint32_t b_stage = (uint32_t)(p.tps * p.b_bytes);
+    const uint32_t bar_base = b_base + (uint32_t)p.nB * b_stage;
+    auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+    auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxA + s); };
+    auto b_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxA + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxA + kMaxB + s); };
+    auto tmem_full_bar = [&](int a, int j) { return bar_base + 8u * (uint32_t)(2 * kMaxA + 2 * kMaxB + 2 * a + j); };
+    auto tmem_empty_bar = [&](int a, int j) { return bar_base + 8u * (uint32_t)(2 * kMaxA + 2 * kMaxB + 4 + 2 * a + j); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxA + 2 * kMaxB + 8);
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
+    // per-tap A descriptor offsets (row shift * 128 B >> 4), then the bias
+    uint32_t *shift_s = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot + 16u - raw));
+    float *bias_s = reinterpret_cast<float *>(smem_raw + (tmem_slot + 16u + 128u - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        // one MMA-issuing warp per accumulator: a stage is free once every issuer's MMAs have read it
+        for (int s = 0; s < p.nA; ++s) {
+            mbar_init(a_full(s), 1);
+            mbar_init(a_empty(s), (uint32_t)p.MT);
+        }
+        for (int s = 0; s < p.nB; ++s) {
+            mbar_init(b_full(s), 1);
+            mbar_init(b_empty(s), (uint32_t)p.MT);
+        }
+        for (int a = 0; a < 2; ++a)
+            for (int j = 0; j < 2; ++j) {
+                mbar_init(tmem_full_bar(a, j), 1);
+                mbar_init(tmem_empty_bar(a, j), (uint32_t)(kEpiWarps / p.MT));
+            }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == 3) {
+        for (int i = lane; i < d.cout_pad; i += 32) bias_s[i] = (d.bias && i < d.Cout) ? d.bias[i] : 0.f;
+        if (lane < RGBD_MAX_TAPS) shift_s[lane] = (uint32_t)((int)p.t_shift[lane] * 8);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // =========================== A producer (halo tiles, residual tiles) ===========================
+        if (lane == 0) {
+            RingPos ra = {0, 0};
+            const bool tr = p.dbg != nullptr && blockIdx.x == 0;
+            long long w_empty = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord(p, tile);
+                for (int g = 0; g < p.ngroups; ++g) {
+                    for (int kb = 0; kb < p.kblocks; ++kb, ra.next(p.nA)) {
+                        const int s = ra.s;
+                        mbar_wait_t(a_empty(s), ra.ph ^ 1u, tr, w_empty);
+                        mbar_expect_tx(a_full(s), (uint32_t)p.a_tx);
+                        tma_load_4d(a_base + (uint32_t)(s * p.a_bytes), &p.amap[p.g_map[g]], a_full(s), kb * kBlockK,
+                                    tc.ox0 + p.g_qx[g], tc.oy0 + p.g_qy[g], tc.n);
+                    }
+                }
+                const int rb = p.res_blocks ? (tc.bn + 63) >> 6 : 0;
+                for (int jb = 0; jb < rb; ++jb, ra.next(p.nA)) {
+                    const int s = ra.s;
+                    mbar_wait(a_empty(s), ra.ph ^ 1u);
+                    mbar_expect_tx(a_full(s), (uint32_t)p.r_tx);
+                    tma_load_4d(a_base + (uint32_t)(s * p.a_bytes), &p.rmap, a_full(s), tc.co0 + jb * kBlockK, tc.ox0,
+                                tc.oy0, tc.n);
+                }
+            }
+            if (tr) p.dbg[0] = w_empty;
+        }
+    } else if (warp == 1) {
+        // =========================== B producer (weights, identity tiles) ===========================
+        if (lane == 0) {
+            RingPos rbp = {0, 0};
+            const bool tr = p.dbg != nullptr && blockIdx.x == 0;
+            long long w_empty = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord(p, tile);
+                for (int g = 0; g < p.ngroups; ++g) {
+                    const int t0 = p.g_first[g], t1 = p.g_first[g + 1];
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        for (int t = t0; t < t1; t += p.tps, rbp.next(p.nB)) {
+                            const int s = rbp.s;
+                            const int n = min(p.tps, t1 - t);
+                            mbar_wait_t(b_empty(s), rbp.ph ^ 1u, tr, w_empty);
+                            mbar_expect_tx(b_full(s), (uint32_t)(n * p.b_bytes));
+                            for (int tt = 0; tt < n; ++tt)
+                                tma_load_3d(b_base + (uint32_t)s * b_stage + (uint32_t)(tt * p.b_bytes), &p.bmap, b_full(s),
+                                            kb * kBlockK, tc.co0, p.t_w[t + tt]);
+                        }
+                    }
+                }
+                const int rb = p.res_blocks ? (tc.bn + 63) >> 6 : 0;
+                for (int jb = 0; jb < rb; ++jb, rbp.next(p.nB)) {
+                    const int s = rbp.s;
+                    mbar_wait(b_empty(s), rbp.ph ^ 1u);
+                    mbar_expect_tx(b_full(s), (uint32_t)p.b_bytes);
+                    tma_load_3d(b_base + (uint32_t)s * b_stage, &p.emap, b_full(s), 0, 0, jb);
+                }
+            }
+            if (tr) p.dbg[1] = w_empty;
+        }
+    } else if (warp == 2 || warp == 3) {
+        // =========================== MMA issuers ===========================
+        // Warp 2 owns accumulator (M tile) 0, warp 3 accumulator 1: one thread cannot issue
+        // tcgen05.mma + barrier traffic fast enough to keep the tensor pipe busy at N <= 128, and two
+        // issuers with one accumulator each keep every accumulator's K order fixed.  The whole warp
+        // walks the loops and waits on the barriers; one elected lane issues.
+        const int j = warp - 2;
+        if (j < p.MT) {
+            int sa = 0, sb = 0;
+            uint32_t pha = 0, phb = 0;
+            int li = 0;
+            const bool tr = p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && j == 0;
+            long long w_tmem = 0, w_a = 0, w_b = 0;
+            const long long t_begin = tr ? clock64() : 0;
+            const uint64_t desc0 = make_smem_desc(0);
+            const int nA = p.nA, nB = p.nB;
+            const uint32_t a_step = (uint32_t)p.a_bytes >> 4, b_step = b_stage >> 4, b_tap = (uint32_t)p.b_bytes >> 4;
+            const int tps = p.tps;
+            const uint32_t a_lo0 = (a_base >> 4) + (uint32_t)(j * 1024), b_lo0 = b_base >> 4;
+            uint32_t a_lo = a_lo0, b_lo = b_lo0;     // descriptor start-address fields of the current ring stages
+            const int kblocks = p.kblocks, ngroups = p.ngroups;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+                const TileCoord tc = tile_coord(p, tile);
+                const int acc = li & 1;
+                const uint32_t use = (uint32_t)(li >> 1);
+                mbar_wait_t(tmem_empty_bar(acc, j), (use & 1u) ^ 1u, tr, w_tmem);   // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t idesc = make_idesc(128, tc.bn);
+                const uint32_t dcol = tmem_base + (uint32_t)(acc * 256 + j * 128);
+                uint32_t started = 0;
+                for (int g = 0; g < ngroups; ++g) {
+                    const int t0 = p.g_first[g], t1 = p.g_first[g + 1];
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait_t(a_full(sa), pha, tr, w_a);
+                        // only the 16-channel groups that hold real input channels (tail block may be short)
+                        const int kleft = d.Cin - kb * kBlockK;
+                        const int nk = kleft >= kBlockK ? 4 : (kleft + 15) >> 4;
+                        for (int t = t0; t < t1; t += tps) {
+                            const int n = min(tps, t1 - t);
+                            mbar_wait_t(b_full(sb), phb, tr, w_b);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                issue_mmas(dcol, desc0 + (uint64_t)(a_lo + shift_s[t]), desc0 + (uint64_t)b_lo, idesc, started, nk);
+                                for (int tt = 1; tt < n; ++tt)
+                                    issue_mmas(dcol, desc0 + (uint64_t)(a_lo + shift_s[t + tt]), desc0 + (uint64_t)(b_lo + tt * b_tap),
+                                               idesc, 1u, nk);
+                                umma_commit(b_empty(sb));   // frees the weight stage once these MMAs have read it
+                            }
+                            __syncwarp();
+                            started = 1;
+                            b_lo += b_step;
+                            if (++sb == nB) {
+                                sb = 0;
+                                phb ^= 1u;
+                                b_lo = b_lo0;
+                            }
+                        }
+                        if (elect_one()) umma_commit(a_empty(sa));
+                        __syncwarp();
+                        a_lo += a_step;
+                        if (++sa == nA) {
+                            sa = 0;
+                            pha ^= 1u;
+                            a_lo = a_lo0;
+                        }
+                    }
+                }
+                const int rb = p.res_blocks ? (tc.bn + 63) >> 6 : 0;
+                for (int jb = 0; jb < rb; ++jb) {
+                    mbar_wait_t(a_full(sa), pha, tr, w_a);
+                    mbar_wait_t(b_full(sb), phb, tr, w_b);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int kvalid = min(kBlockK, tc.bn - jb * kBlockK);
+                        issue_mmas(dcol, desc0 + (uint64_t)a_lo, desc0 + (uint64_t)b_lo, idesc, started, (kvalid + 15) >> 4);
+                        umma_commit(b_empty(sb));
+                        umma_commit(a_empty(sa));
+                    }
+                    __syncwarp();
+                    started = 1;
+                    b_lo += b_step;
+                    if (++sb == nB) {
+                        sb = 0;
+                        phb ^= 1u;
+                        b_lo = b_lo0;
+                    }
+                    a_lo += a_step;
+                    if (++sa == nA) {
+                        sa = 0;
+                        pha ^= 1u;
+                        a_lo = a_lo0;
+                    }
+                }
+                if (elect_one()) umma_commit(tmem_full_bar(acc, j));
+                __syncwarp();
+            }
+            if (tr) {
+                p.dbg[2] = w_tmem;
+                p.dbg[3] = w_a;
+                p.dbg[4] = w_b;
+                p.dbg[5] = clock64() - t_begin;
+                p.dbg[6] = li;
+            }
+        }
+    } else if (warp >= kFirstEpiWarp) {
+        // ============ epilogue: TMEM -> registers -> NHWC global ============
+        const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+        const int set = (warp - kFirstEpiWarp) >> 2;     // 0 / 1
+        const int j = p.MT == 2 ? set : 0;               // accumulator (M tile) this warp drains
+        const int cfirst = p.MT == 2 ? 0 : set;          // MT == 1: the two warp sets split the 16-column chunks
+        const int cstep = p.MT == 2 ? 1 : 2;
+        const int pos = j * 128 + quad * 32 + lane;      // position inside the super-tile
+        const int ty = pos / p.P, tx = pos - ty * p.P;
+        TOut *y = reinterpret_cast<TOut *>(d.y);
+        TOut *y2 = reinterpret_cast<TOut *>(d.y2);
+        const bf16 *res = reinterpret_cast<const bf16 *>(d.res);
+        const bf16 *mul = reinterpret_cast<const bf16 *>(d.mul);
+        constexpr int kVecOut = 16 / (int)sizeof(TOut);   // elements per 16 B
+        const bool y_vec = ((d.y_cstride | d.y_coff) % kVecOut) == 0;
+        const bool y2_vec = ((d.y2_cstride | d.y2_coff) % kVecOut) == 0;
+        const bool res_vec = ((d.res_cstride | d.res_coff) & 7) == 0;
+        const bool mul_vec = ((d.mul_cstride | d.mul_coff) & 7) == 0;
+        // residual handled here only when it did not ride on the tensor core
+        const bool res_direct = res != nullptr && kEpi != RGBD_EPI_BILERP && p.res_blocks == 0;
+        int li = 0;
+        const bool tr = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == kFirstEpiWarp * 32;
+        long long w_full = 0;
+        const long long t_begin = tr ? clock64() : 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+            const TileCoord tc = tile_coord(p, tile);
+            const int acc = li & 1;
+            const uint32_t use = (uint32_t)(li >> 1);
+            const int sy = tc.oy0 + ty, sx = tc.ox0 + tx;    // site in the Hs x Ws output lattice
+            const bool valid = ty < p.R && tx < p.TW && sy < d.Hs && sx < d.Ws;
+            const int oy = sy * d.o_step + d.o_off_y, ox = sx * d.o_step + d.o_off_x;
+            const int64_t opix = ((int64_t)tc.n * d.Ho + oy) * d.Wo + ox;
+            const int nchunks = tc.bn >> 4;
+            // gate / late-residual operands of this thread's pixel are requested BEFORE the accumulator
+            // is ready, one 16-column chunk ahead of their use
+            uint4 pr[2], pm[2];
+            auto prefetch = [&](int c) {
+                const int co = tc.co0 + c * 16;
+                const bool on = valid && c < nchunks && d.Cout - co >= 16;
+                pr[0] = pr[1] = pm[0] = pm[1] = make_uint4(0, 0, 0, 0);
+                if (on && res_direct && res_vec) {
+                    const uint4 *q = reinterpret_cast<const uint4 *>(res + opix * d.res_cstride + d.res_coff + co);
+                    pr[0] = q[0];
+                    pr[1] = q[1];
+                }
+                if (kGate && on && mul_vec) {
+                    const uint4 *q = reinterpret_cast<const uint4 *>(mul + opix * d.mul_cstride + d.mul_coff + co);
+                    pm[0] = q[0];
+                    pm[1] = q[1];
+                }
+            };
+            if (kGate || res_direct) prefetch(cfirst);
+            int by0 = 0, by1 = 0, bx0 = 0, bx1 = 0;
+            float ly = 0.f, lx = 0.f;
+            if (kEpi == RGBD_EPI_BILERP && valid) {
+                bilerp_axis(oy, d.res_H, d.Ho, by0, by1, ly);
+                bilerp_axis(ox, d.res_W, d.Wo, bx0, bx1, lx);
+            }
+            mbar_wait_t(tmem_full_bar(acc, j), use & 1u, tr, w_full);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + j * 128);
+            uint32_t r0[16], r1[16];
+            auto process = [&](int c, const uint32_t *rv) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rv[i]);
+                const int co = tc.co0 + c * 16;
+                const int nvalid = d.Cout - co;
+                uint4 cr[2] = {pr[0], pr[1]}, cm[2] = {pm[0], pm[1]};
+                if ((kGate || res_direct) && c + cstep < nchunks) prefetch(c + cstep);
+                if (valid && nvalid > 0) {
+                    const bool full16 = nvalid >= 16;
+                    {
+                        const float4 *bs = reinterpret_cast<const float4 *>(bias_s + co);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 b4 = bs[i];
+                            v[4 * i] += b4.x;
+                            v[4 * i + 1] += b4.y;
+                            v[4 * i + 2] += b4.z;
+                            v[4 * i + 3] += b4.w;
+                        }
+                    }
+                    float r[16];
+                    if (res_direct) {
+                        if (res_vec && full16) {
+                            unpack8(cr[0], r);
+                            unpack8(cr[1], r + 8);
+                        } else {
+                            load16_bf16(res + opix * d.res_cstride + d.res_coff + co, false, nvalid, r);
+                        }
+                    }
+                    if (kGate) {
+                        float m[16];
+                        if (mul_vec && full16) {
+                            unpack8(cm[0], m);
+                            unpack8(cm[1], m + 8);
+                        } else {
+                            load16_bf16(mul + opix * d.mul_cstride + d.mul_coff + co, false, nvalid, m);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = m[i] * __fdividef(1.0f, 1.0f + __expf(-v[i]));
+                        if (res_direct) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] += r[i];
+                        }
+                    } else if (kEpi == RGBD_EPI_LINEAR) {
+                        if (res_direct) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] += r[i];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = act_fn(v[i], d.act);
+                    } else {  // RGBD_EPI_BILERP
+                        const int64_t rbase = (int64_t)tc.n * d.res_H * d.res_W;
+                        const int cc = d.res_coff + co;
+                        float a00[16], a01[16], a10[16], a11[16];
+                        load16_bf16(res + (rbase + (int64_t)by0 * d.res_W + bx0) * d.res_cstride + cc, res_vec, nvalid, a00);
+                        load16_bf16(res + (rbase + (int64_t)by0 * d.res_W + bx1) * d.res_cstride + cc, res_vec, nvalid, a01);
+                        load16_bf16(res + (rbase + (int64_t)by1 * d.res_W + bx0) * d.res_cstride + cc, res_vec, nvalid, a10);
+                        load16_bf16(res + (rbase + (int64_t)by1 * d.res_W + bx1) * d.res_cstride + cc, res_vec, nvalid, a11);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float up = (1.f - ly) * ((1.f - lx) * a00[i] + lx * a01[i]) +
+                                             ly * ((1.f - lx) * a10[i] + lx * a11[i]);
+                            v[i] = act_fn(v[i] + up, d.act);
+                        }
+                    }
+                    store16<TOut>(y + opix * d.y_cstride + d.y_coff + co, y_vec, nvalid, v);
+                    if (y2) store16<TOut>(y2 + opix * d.y2_cstride + d.y2_coff + co, y2_vec, nvalid, v);
+                }
+                        };
+            if (cfirst < nchunks) tmem_ld16_issue(trow + (uint32_t)(cfirst * 16), r0);
+            for (int c = cfirst; c < nchunks; c += 2 * cstep) {
+                // the next chunk's accumulator columns travel while this chunk is processed
+                tmem_ld_wait(r0);
+                if (c + cstep < nchunks) tmem_ld16_issue(trow + (uint32_t)((c + cstep) * 16), r1);
+                process(c, r0);
+                if (c + cstep < nchunks) {
+                    tmem_ld_wait(r1);
+                    if (c + 2 * cstep < nchunks) tmem_ld16_issue(trow + (uint32_t)((c + 2 * cstep) * 16), r0);
+                    process(c + cstep, r1);
+                }
+            }
+            // all of this warp's tcgen05.ld have completed: hand the buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc, j));
+        }
+        if (tr) {
+            p.dbg[7] = w_full;
+            p.dbg[8] = clock64() - t_begin;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int encode_map(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
+               const cuuint32_t *box) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        rgbd_set_error("conv_tc: cuTensorMapEncodeTiled unavailable");
+        return RGBD_E_CUDA;
+    }
+    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), dims,
+                     strides_bytes, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        rgbd_set_error("conv_tc: cuTensorMapEncodeTiled failed (%d) rank %d dims %llu %llu %llu box %u %u %u", (int)r,
+                       rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                       box[0], box[1], box[2]);
+        return RGBD_E_CUDA;
+    }
+    return RGBD_OK;
+}
+
+inline int floordiv2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
+
+// identity tiles for the residual-through-MMA trick: E[jb][n][k] = (n == 64 * jb + k)
+__device__ __nv_bfloat16 g_identity[2 * 128 * kBlockK];
+__global__ void identity_init_kernel() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * 128 * kBlockK) {
+        const int k = i % kBlockK, n = (i / kBlockK) % 128, jb = i / (kBlockK * 128);
+        g_identity[i] = __float2bfloat16_rn(n == jb * kBlockK + k ? 1.f : 0.f);
+    }
+}
+const void *identity_ptr() {
+    static void *ptr[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!ptr[dev]) {
+        void *q = nullptr;
+        if (cudaGetSymbolAddress(&q, g_identity) != cudaSuccess) return nullptr;
+        identity_init_kernel<<<(2 * 128 * kBlockK + 255) / 256, 256>>>();
+        if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;
+        ptr[dev] = q;
+    }
+    return ptr[dev];
+}
+
+}  // namespace
+
+struct rgbd_conv_tc_plan {
+    HParams p;
+    dim3 grid;
+    size_t smem;
+    int out_f32;
+    int epi;
+};
+
+extern "C" int rgbd_conv_validate(const rgbd_conv_desc *d);
+
+extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad, rgbd_conv_tc_plan **out) {
+    int rc = rgbd_conv_validate(d);
+    if (rc) return rc;
+    RGBD_CHECK_ARG(out != nullptr, "null out");
+    RGBD_CHECK_ARG(d->x_dtype == RGBD_DT_BF16, "tensor-core path needs bf16 activations");
+    RGBD_CHECK_ARG(d->in_scale == nullptr, "in_scale is not supported on the tensor-core path (pre-scale the input)");
+    RGBD_CHECK_ARG((d->x_cstride & 7) == 0 && (d->x_coff & 7) == 0, "x view must be 16-byte aligned (cstride, coff % 8)");
+    RGBD_CHECK_ARG(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->w & 15) == 0, "x / w base must be 16-byte aligned");
+    RGBD_CHECK_ARG(cin_pad >= d->Cin && (cin_pad % kBlockK) == 0, "cin_pad must be a multiple of 64 >= Cin");
+    RGBD_CHECK_ARG(d->i_step == 1 || d->i_step == 2, "i_step must be 1 or 2");
+    RGBD_CHECK_ARG(d->cout_pad <= kMaxBias, "cout_pad too large");
+    RGBD_CHECK_ARG((int64_t)d->N * d->Ho * d->Wo < 2147483647LL, "too many output pixels");
+
+    rgbd_conv_tc_plan *pl = new (std::nothrow) rgbd_conv_tc_plan();
+    if (!pl) {
+        rgbd_set_error("conv_tc: out of host memory");
+        return RGBD_E_INVALID;
+    }
+    HParams &p = pl->p;
+    p.d = *d;
+    p.dbg = nullptr;
+    if (const char *e = getenv("RGBD_TC_TRACE")) p.dbg = (long long *)strtoull(e, nullptr, 0);
+
+    // ---- tap groups: taps that read the same input lattice (parity class when i_step == 2) ----
+    const int st = d->i_step;
+    int tq_y[RGBD_MAX_TAPS], tq_x[RGBD_MAX_TAPS], tg[RGBD_MAX_TAPS];
+    for (int t = 0; t < d->ntaps; ++t) {
+        if (st == 1) {
+            tg[t] = 0;
+            tq_y[t] = d->dy[t];
+            tq_x[t] = d->dx[t];
+        } else {
+            const int qy = floordiv2(d->dy[t]), qx = floordiv2(d->dx[t]);
+            tg[t] = (d->dy[t] - 2 * qy) * 2 + (d->dx[t] - 2 * qx);
+            tq_y[t] = qy;
+            tq_x[t] = qx;
+        }
+    }
+    int order[RGBD_MAX_TAPS], nord = 0;
+    int ext_x = 1, ext_y = 1;
+    p.ngroups = 0;
+    for (int g = 0; g < 4; ++g) {
+        int qy0 = 127, qy1 = -127, qx0 = 127, qx1 = -127, cnt = 0;
+        for (int t = 0; t < d->ntaps; ++t)
+            if (tg[t] == g) {
+                qy0 = tq_y[t] < qy0 ? tq_y[t] : qy0;
+                qy1 = tq_y[t] > qy1 ? tq_y[t] : qy1;
+                qx0 = tq_x[t] < qx0 ? tq_x[t] : qx0;
+                qx1 = tq_x[t] > qx1 ? tq_x[t] : qx1;
+                ++cnt;
+            }
+        if (!cnt) continue;
+        const int gi = p.ngroups++;
+        p.g_map[gi] = (int8_t)g;
+        p.g_qy[gi] = (int8_t)qy0;
+        p.g_qx[gi] = (int8_t)qx0;
+        p.g_first[gi] = (int8_t)nord;
+        for (int t = 0; t < d->ntaps; ++t)
+            if (tg[t] == g) order[nord++] = t;
+        ext_x = (qx1 - qx0 + 1) > ext_x ? (qx1 - qx0 + 1) : ext_x;
+        ext_y = (qy1 - qy0 + 1) > ext_y ? (qy1 - qy0 + 1) : ext_y;
+    }
+    p.g_first[p.ngroups] = (int8_t)nord;
+    for (int g = p.ngroups + 1; g <= kMaxGroups; ++g) p.g_first[g] = (int8_t)nord;
+
+    p.kblocks = (d->Cin + kBlockK - 1) / kBlockK;
+    // N tile <= 128: two accumulators (M tiles) x two buffers fit the 512 TMEM columns
+    const int ntiles = (d->cout_pad + 127) / 128;
+    p.BN = ((d->cout_pad + ntiles - 1) / ntiles + 15) / 16 * 16;
+    p.n_ntiles = (d->cout_pad + p.BN - 1) / p.BN;
+    p.b_bytes = p.BN * 128;
+
+    // residual through the tensor core: plain residual adds on the full output lattice
+    const bool res_mma = d->res != nullptr && d->epi == RGBD_EPI_LINEAR && d->o_step == 1 &&
+                         ((d->res_cstride | d->res_coff) & 7) == 0 && ((uintptr_t)d->res & 15) == 0;
+    p.res_blocks = res_mma ? (p.BN + 63) / 64 : 0;
+
+    // ---- super-tile geometry: TW useful columns, R rows, pitch P = TW + ext_x - 1, R * P <= 256 ----
+    // cost model (cycles per useful output site): MMA issue floor vs L2 -> shared-memory fetch; it does
+    // not look at the batch size, so the geometry (and with it nothing numerically relevant) is the
+    // same for every N
+    double best = -1;
+    const double cin_frac = (double)d->Cin / (double)(p.kblocks * kBlockK);
+    for (int TW = 1; TW <= d->Ws && TW + ext_x - 1 <= 256; ++TW) {
+        const int P = TW + ext_x - 1;
+        for (int MT = 1; MT <= 2; ++MT) {
+            int R = MT * 128 / P;
+            if (R > d->Hs) R = d->Hs;
+            if (R < 1) continue;
+            if (MT == 2 && R * P <= 128) continue;
+            const int box_rows = R + ext_y - 1;
+            if (box_rows > 256) continue;
+            long halo_rows = (long)box_rows * P + ext_x - 1;
+            const long need_rows = (long)MT * 128 + (long)(ext_y - 1) * P + ext_x - 1;
+            if (need_rows > halo_rows) halo_rows = need_rows;
+            const long a_bytes = (halo_rows * 128 + 1023) / 1024 * 1024;
+            if (a_bytes > kMaxAStage) continue;
+            const double tiles = (double)((d->Ws + TW - 1) / TW) * (double)((d->Hs + R - 1) / R);
+            const double mma = (double)MT * (d->ntaps * p.kblocks + p.res_blocks) * 4.0 * (p.BN / 2.0);
+            const double l2 = ((double)p.ngroups * p.kblocks * box_rows * P * 128.0 * cin_frac +
+                               (double)d->ntaps * p.kblocks * p.b_bytes + (double)p.res_blocks * (R * P * 128.0 + p.b_bytes)) /
+                              42.0;
+            const double per_tile = (mma > l2 ? mma : l2) + 0.15 * (mma < l2 ? mma : l2) + 1500.0;
+            const double cost = tiles * per_tile;
+            if (best < 0 || cost < best) {
+                best = cost;
+                p.TW = TW;
+                p.R = R;
+                p.P = P;
+                p.MT = MT;
+                p.box_rows = box_rows;
+            }
+        }
+    }
+    if (best < 0) {
+        rgbd_set_error("conv_tc: no tile geometry for Hs %d Ws %d ext %d x %d", d->Hs, d->Ws, ext_y, ext_x);
+        delete pl;
+        return RGBD_E_INVALID;
+    }
+    p.tiles_x = (d->Ws + p.TW - 1) / p.TW;
+    p.tiles_y = (d->Hs + p.R - 1) / p.R;
+    {
+        // the stage must hold both the halo tile and the 128 * MT rows the MMAs address (+ tap shift)
+        long rows = (long)p.box_rows * p.P + ext_x - 1;
+        const long need = (long)p.MT * 128 + (long)(ext_y - 1) * p.P + ext_x - 1;
+        if (need > rows) rows = need;
+        p.a_bytes = (int)((rows * 128 + 1023) / 1024 * 1024);
+    }
+    p.a_tx = p.box_rows * p.P * 128;
+    p.r_tx = p.R * p.P * 128;
+    for (int i = 0; i < nord; ++i) {
+        const int t = order[i];
+        int gi = 0;
+        while (p.g_map[gi] != tg[t]) ++gi;
+        p.t_shift[i] = (int16_t)((tq_y[t] - p.g_qy[gi]) * p.P + (tq_x[t] - p.g_qx[gi]));
+        p.t_w[i] = d->wtap[t];
+    }
+    // Weight stages hold up to 3 consecutive taps (<= 36 KB): one barrier round trip + commit per stage
+    // costs an issuing thread ~600 cycles, which 4 MMAs per accumulator do not cover.
+    int max_group_taps = 1;
+    for (int g = 0; g < p.ngroups; ++g) {
+        const int n = p.g_first[g + 1] - p.g_first[g];
+        max_group_taps = n > max_group_taps ? n : max_group_taps;
+    }
+    p.tps = 36 * 1024 / p.b_bytes;
+    if (p.tps > 3) p.tps = 3;
+    if (p.tps > max_group_taps) p.tps = max_group_taps;
+    if (p.tps < 1) p.tps = 1;
+    // ring depths: 2 A stages (more when affordable), at least 2 weight stages
+    p.nA = 2;
+    while (p.tps > 1 && (kRingBudget - p.nA * p.a_bytes) / (p.tps * p.b_bytes) < 2) --p.tps;
+    const int b_stage = p.tps * p.b_bytes;
+    p.nB = (kRingBudget - p.nA * p.a_bytes) / b_stage;
+    if (p.nB > kMaxB) p.nB = kMaxB;
+    if (p.nB < 2) {
+        rgbd_set_error("conv_tc: ring budget too small (a_bytes %d b_bytes %d)", p.a_bytes, p.b_bytes);
+        delete pl;
+        return RGBD_E_INVALID;
+    }
+    const int a_iters = p.kblocks * p.ngroups + p.res_blocks;
+    const int nb_keep = p.tps > 1 ? 2 : 5;
+    while (p.nA < kMaxA && p.nA < a_iters + 1 &&
+           (p.nA + 1) * p.a_bytes + (p.nB < nb_keep ? p.nB : nb_keep) * b_stage <= kRingBudget) {
+        ++p.nA;
+        const int nb = (kRingBudget - p.nA * p.a_bytes) / b_stage;
+        if (nb < p.nB) p.nB = nb;
+    }
+    const long total = (long)d->N * p.tiles_x * p.tiles_y * p.n_ntiles;
+    RGBD_CHECK_ARG(total < 2147483647L, "too many tiles");
+    p.total_tiles = (int)total;
+    pl->smem = (size_t)p.nA * p.a_bytes + (size_t)p.nB * p.tps * p.b_bytes + 1024 /*align*/ +
+               8 * (2 * kMaxA + 2 * kMaxB + 8) + 16 + 128 + 4 * (size_t)d->cout_pad + 64;
+    if (pl->smem < (size_t)kMinSmem) pl->smem = kMinSmem;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
+            num_sms = 148;
+    }
+    pl->grid = dim3((unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms));
+    pl->out_f32 = d->y_dtype == RGBD_DT_F32;
+    pl->epi = d->epi;
+
+    // A tensor maps: one per input parity class (i_step == 2) or a single one
+    const char *xb = reinterpret_cast<const char *>(d->x);
+    for (int ry = 0; ry < st; ++ry)
+        for (int rx = 0; rx < st; ++rx) {
+            const int Hsub = (d->H - ry + st - 1) / st, Wsub = (d->W - rx + st - 1) / st;
+            if (Hsub <= 0 || Wsub <= 0) continue;
+            cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)Wsub, (cuuint64_t)Hsub, (cuuint64_t)d->N};
+            cuuint64_t strides[3] = {(cuuint64_t)st * d->x_cstride * 2, (cuuint64_t)st * d->W * d->x_cstride * 2,
+                                     (cuuint64_t)d->H * d->W * d->x_cstride * 2};
+            cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)p.P, (cuuint32_t)p.box_rows, 1};
+            const void *basep = xb + ((int64_t)(ry * d->W + rx) * d->x_cstride + d->x_coff) * 2;
+            rc = encode_map(&p.amap[ry * st + rx], basep, 4, dims, strides, box);
+            if (rc) {
+                delete pl;
+                return rc;
+            }
+        }
+    for (int i = st * st; i < 4; ++i) p.amap[i] = p.amap[0];
+    // B tensor map over the packed weights [taps_total][cout_pad][cin_pad] (taps_total >= max wtap + 1)
+    int max_tap = 0;
+    for (int t = 0; t < d->ntaps; ++t) max_tap = d->wtap[t] > max_tap ? d->wtap[t] : max_tap;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)d->cout_pad, (cuuint64_t)(max_tap + 1)};
+        cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * d->cout_pad * 2};
+        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)p.BN, 1};
+        rc = encode_map(&p.bmap, d->w, 3, dims, strides, box);
+        if (rc) {
+            delete pl;
+            return rc;
+        }
+    }
+    p.rmap = p.amap[0];
+    p.emap = p.bmap;
+    if (p.res_blocks) {
+        cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->N};
+        cuuint64_t strides[3] = {(cuuint64_t)d->res_cstride * 2, (cuuint64_t)d->Wo * d->res_cstride * 2,
+                                 (cuuint64_t)d->Ho * d->Wo * d->res_cstride * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)p.P, (cuuint32_t)p.R, 1};
+        rc = encode_map(&p.rmap, reinterpret_cast<const char *>(d->res) + (int64_t)d->res_coff * 2, 4, dims, strides, box);
+        if (!rc) {
+            const void *idp = identity_ptr();
+            if (!idp) {
+                rgbd_set_error("conv_tc: identity tile unavailable");
+                rc = RGBD_E_CUDA;
+            } else {
+                cuuint64_t edims[3] = {(cuuint64_t)kBlockK, 128, 2};
+                cuuint64_t estr[2] = {(cuuint64_t)kBlockK * 2, (cuuint64_t)kBlockK * 128 * 2};
+                cuuint32_t ebox[3] = {(cuuint32_t)kBlockK, (cuuint32_t)p.BN, 1};
+                rc = encode_map(&p.emap, idp, 3, edims, estr, ebox);
+            }
+        }
+        if (rc) {
+            delete pl;
+            return rc;
+        }
+    }
+    static bool configured = false;
+    if (!configured) {
+        const int cap = 200 * 1024;
+        cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(conv_halo_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(conv_halo_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(conv_halo_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        configured = true;
+    }
+    if (getenv("RGBD_TC_VERBOSE"))
+        fprintf(stderr, "conv_halo: %dx%d taps %d Cin %d Cout %d | TW %d R %d P %d MT %d box_rows %d groups %d kb %d BN %d nA %d nB %d tps %d a %d b %d res %d tiles %d smem %zu\n",
+                d->Hs, d->Ws, d->ntaps, d->Cin, d->Cout, p.TW, p.R, p.P, p.MT, p.box_rows, p.ngroups, p.kblocks, p.BN, p.nA, p.nB, p.tps,
+                p.a_bytes, p.b_bytes, p.res_blocks, p.total_tiles, pl->smem);
+    *out = pl;
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_conv_tc_run(const rgbd_conv_tc_plan *pl, void *stream) {
+    RGBD_CHECK_ARG(pl != nullptr, "null plan");
+    cudaStream_t st = (cudaStream_t)stream;
+#define RGBD_TC_LAUNCH(T, E) conv_halo_kernel<T, E><<<pl->grid, kThreads, pl->smem, st>>>(pl->p)
+    if (pl->out_f32) {
+        if (pl->epi == RGBD_EPI_GATE) RGBD_TC_LAUNCH(float, 1);
+        else if (pl->epi == RGBD_EPI_BILERP) RGBD_TC_LAUNCH(float, 2);
+        else RGBD_TC_LAUNCH(float, 0);
+    } else {
+        if (pl->epi == RGBD_EPI_GATE) RGBD_TC_LAUNCH(__nv_bfloat16, 1);
+        else if (pl->epi == RGBD_EPI_BILERP) RGBD_TC_LAUNCH(__nv_bfloat16, 2);
+        else RGBD_TC_LAUNCH(__nv_bfloat16, 0);
+    }
+#undef RGBD_TC_LAUNCH
+    RGBD_LAUNCH_CHECK();
+    return RGBD_OK;
+}
+
+extern "C" void rgbd_conv_tc_plan_destroy(rgbd_conv_tc_plan *pl) { delete pl; }

@@ -321,6 +321,12 @@ TC_CONVS = [
     ("deconv5s2_192", lambda: nn.ConvTranspose2d(192, 192, 5, 2, padding=2, output_padding=1), (1, 192, 9, 11)),
     ("deconv5s2_to3", lambda: nn.ConvTranspose2d(192, 3, 5, 2, padding=2, output_padding=1), (2, 192, 16, 16)),
     ("deconv3s1_960_640", lambda: nn.ConvTranspose2d(960, 640, 3, 1, padding=1), (1, 960, 8, 10)),
+    # two-accumulator super-tiles, several tiles per row, halo rows shared between the M tiles
+    ("3x3_96_96_wide", lambda: nn.Conv2d(96, 96, 3, 1, 1), (2, 96, 64, 80)),
+    ("1x1_192_96_wide", lambda: nn.Conv2d(192, 96, 1), (1, 192, 64, 80)),
+    ("5x5_224_128_latent", lambda: nn.Conv2d(224, 128, 5, 1, 2), (2, 224, 32, 40)),
+    ("5x5s2_192_192_wide", lambda: nn.Conv2d(192, 192, 5, 2, 2), (1, 192, 64, 96)),
+    ("deconv5s2_320_192_latent", lambda: nn.ConvTranspose2d(320, 192, 5, 2, padding=2, output_padding=1), (1, 320, 32, 40)),
 ]
 
 
@@ -353,6 +359,15 @@ def test_conv_tc_epilogues():
     assert rel_err(run_conv_tc(mod, x, act=1, res=res), F.relu(v + rb)) < tol
     assert rel_err(run_conv_tc(mod, x, epi=1, mul=mul, res=res), rb + mb * torch.sigmoid(v)) < tol
     assert rel_err(run_conv_tc(mod, x, epi=1, mul=mul), mb * torch.sigmoid(v)) < tol
+    # residual riding on the tensor core (identity B tile): several N tiles, ragged last residual block
+    for cin, cout, hw in ((96, 192, (40, 48)), (160, 320, (32, 40)), (48, 40, (9, 11))):
+        m3 = nn.Conv2d(cin, cout, 1).eval()
+        x3, r3 = torch.randn(2, cin, *hw), torch.randn(2, cout, *hw)
+        assert rel_err(run_conv_tc(m3, x3, act=1, res=r3), F.relu(bf16_ref(m3, x3) + r3.bfloat16().float())) < tol
+        assert rel_err(run_conv_tc(m3, x3, res=r3, out_dtype=torch.bfloat16), bf16_ref(m3, x3) + r3.bfloat16().float()) < 6e-3
+    m4 = nn.Conv2d(96, 96, 3, 1, 1).eval()
+    x4, r4 = torch.randn(1, 96, 30, 44), torch.randn(1, 96, 30, 44)
+    assert rel_err(run_conv_tc(m4, x4, res=r4), bf16_ref(m4, x4) + r4.bfloat16().float()) < tol
     # SE gate folded through the separate scale pass (bf16 rounding of the scaled input)
     scale = torch.rand(2, 96) + 0.5
     want = bf16_ref(mod, (x.bfloat16().float() * scale[:, :, None, None]))
