@@ -191,37 +191,28 @@ def run_b200(args):
     sl = [slice(i * B, (i + 1) * B) for i in range(S)]
     host_out = [(torch.empty((B, 3, Hp, Wp)).pin_memory(), torch.empty((B, 1, Hp, Wp)).pin_memory()) for _ in range(S)]
 
-    def run_slots(inputs, to_host):
-        hs = [net.compress_async(inputs[i][0], inputs[i][1], slot=i) for i in range(S)]
-        cs, ds = [], []
-        for i in range(S):
-            c = hs[i].result()
-            cs.append(c)
-            ds.append(net.decompress_async(c["r_strings"], c["d_strings"], c["shape"], slot=i))
-        outs = []
-        for i in range(S):
-            r = ds[i].result(clone=False)
-            if to_host:   # D2H of the reconstruction into pinned host buffers
-                with torch.cuda.stream(ds[i].stream):
-                    host_out[i][0].copy_(r["x_hat"]["r"], non_blocking=True)
-                    host_out[i][1].copy_(r["x_hat"]["d"], non_blocking=True)
-                outs.append(host_out[i])
-            else:
-                outs.append((r["x_hat"]["r"], r["x_hat"]["d"]))
-        if to_host:
-            for i in range(S):
-                ds[i].stream.synchronize()
-        return cs, outs
+    # Round-trip pipeline (rgbd_b200.pipeline): S compress jobs and S decompress jobs in flight, each on
+    # its own stream + launch plan, so the decoder's serial rANS chain of batch k hides behind the
+    # convolutions of batches k+1..; one step = S batches of B pairs, every pair compressed AND
+    # decompressed inside the timed region.
+    from rgbd_b200.pipeline import RoundTripPipeline
+    pipe = RoundTripPipeline(net, S)
 
-    def step_device():
-        return run_slots([(rgb_d[sl[i]], depth_d[sl[i]]) for i in range(S)], False)
+    def steps_device(k):
+        jobs = [(rgb_d[sl[i % S]], depth_d[sl[i % S]]) for i in range(k * S)]
+        return pipe.run(jobs)
 
-    def step_e2e():
-        ins = []
-        for i in range(S):
-            with torch.cuda.stream(net._slot_stream(i)):
-                ins.append((rgb_h[sl[i]].to(dev, non_blocking=True), depth_h[sl[i]].to(dev, non_blocking=True)))
-        return run_slots(ins, True)
+    def steps_e2e(k):
+        def stage_input(j, slot, stream):    # H2D of this batch's images from pinned host memory
+            return rgb_h[sl[slot]].to(dev, non_blocking=True), depth_h[sl[slot]].to(dev, non_blocking=True)
+
+        def sink(j, slot, stream, x_r, x_d):  # D2H of the reconstruction into pinned host buffers
+            host_out[slot][0].copy_(x_r, non_blocking=True)
+            host_out[slot][1].copy_(x_d, non_blocking=True)
+
+        res = pipe.run([None] * (k * S), stage_input=stage_input, sink=sink)
+        torch.cuda.synchronize(dev)
+        return res
 
     def barrier():
         if world > 1:
@@ -232,9 +223,7 @@ def run_b200(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = None
-        for _ in range(steps):
-            out = fn()
+        out = fn(steps)     # returns once every job of the K steps has completed (all slots drained)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -243,27 +232,31 @@ def run_b200(args):
         return float(ms.item()), out
 
     W_, K = max(3, args.warmup), max(1, args.steps)
-    for _ in range(W_):
-        step_device()
+    steps_device(W_)
     # L2 note: one step streams > 1 GB of activations per image through HBM, far beyond the 126 MB L2,
     # so consecutive steps cannot serve each other from cache (no explicit flush needed).
     L.load().rgbd_launch_count(1)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, (cs, outs) = timed(step_device, K)
+    ms, res = timed(steps_device, K)
+    cs = [c for _, c, _ in res]
+    outs = [xs for _, _, xs in res]
+    last_slots = [j % S for j, _, _ in res]
     launches = int(L.load().rgbd_launch_count(1))
     clocks = sampler.stop() if rank == 0 else None
     pairs_per_step = S * B
     value = world * pairs_per_step * K / (ms / 1e3)
     stats = new_stats()
-    for i in range(S):
+    for i, slot in enumerate(last_slots):
         add_pair_stats(stats, cs[i]["r_strings"], cs[i]["d_strings"],
-                       rgb_d[sl[i]][:, :, :args.height, :args.width], depth_d[sl[i]][:, :, :args.height, :args.width],
+                       rgb_d[sl[slot]][:, :, :args.height, :args.width], depth_d[sl[slot]][:, :, :args.height, :args.width],
                        outs[i][0][:, :, :args.height, :args.width], outs[i][1][:, :, :args.height, :args.width])
 
-    step_e2e()
-    ms_e2e, (cs2, outs2) = timed(step_e2e, K)
+    steps_e2e(1)
+    ms_e2e, res2 = timed(steps_e2e, K)
+    cs2 = [c for _, c, _ in res2]
+    outs2 = [xs for _, _, xs in res2]
     e2e_value = world * pairs_per_step * K / (ms_e2e / 1e3)
     stream_bytes = sum(len(x) for c in cs2 for key in ("r_strings", "d_strings") for grp in c[key] for x in grp)
     h2d = rgb_h.numel() * 4 + depth_h.numel() * 4 + stream_bytes
@@ -271,7 +264,7 @@ def run_b200(args):
 
     # roofline of the dominant kernel family (the implicit-GEMM conv): per-launch CUDA events on the
     # launching stream, over the same workload
-    roof = conv_roofline(net, B, Hp, Wp, dev)
+    roof = conv_roofline(net, B, Hp, Wp, dev, dec_slot=S)
     stats = summarize(allreduce_stats(stats, dev))
     if rank == 0:
         pk, pk_src = peaks()
@@ -282,7 +275,7 @@ def run_b200(args):
             "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": f"ELIC_united compress+decompress, {world}x{S}x{B} pairs/step of "
                                    f"{args.height}x{args.width} (padded {Hp}x{Wp}), preset {args.preset}, "
-                                   f"weights calibrated random-init", "pairs_per_gpu": S * B, "batch": B, "slots_in_flight": S, "precision": args.precision, "cuda_graphs": bool(args.graphs),
+                                   f"weights calibrated random-init", "pairs_per_gpu": S * B, "batch": B, "slots_in_flight": S, "schedule": "pipelined: S compress + S decompress jobs in flight (rgbd_b200.pipeline)", "precision": args.precision, "cuda_graphs": bool(args.graphs),
                        "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
                        "parallelism": f"dp{world} (images sharded, no data-path collective)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
@@ -303,13 +296,13 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def conv_roofline(net, B, Hp, Wp, dev):
+def conv_roofline(net, B, Hp, Wp, dev, dec_slot=0):
     """Algorithmic conv flops / sum of conv launch durations for one encoder + decoder pass."""
     import ctypes as C
     import torch
     total_ms, total_flops, n = 0.0, 0.0, 0
     with torch.cuda.device(dev):
-        for prog in (net._program("encoder", B, Hp, Wp), net._program("decoder", B, Hp // 64, Wp // 64)):
+        for prog in (net._program("encoder", B, Hp, Wp), net._program("decoder", B, Hp // 64, Wp // 64, slot=dec_slot)):   # plans the timed run used: their buffers hold real streams
             sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             evs = []
             for op in prog.ops:

@@ -43,6 +43,7 @@ constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);   // 384
 constexpr int kBlockK = 64;                        // bf16 elements = 128 B = one swizzle row
 constexpr int kMaxA = 4, kMaxB = 8;                // ring depths
 constexpr int kRingBudget = 160 * 1024;            // A ring + B ring; leaves room for a rANS block on the SM
+constexpr int kStageBytes = kEpiWarps * 2048;      // per epilogue warp: 32 rows x 64 B output transpose tile
 constexpr int kMaxAStage = 52 * 1024;              // halo tile (one channel block)
 constexpr int kMinSmem = 120 * 1024;               // > half an SM: never two of these CTAs on one SM (512 TMEM columns each)
 constexpr uint32_t kTmemCols = 512;
@@ -56,7 +57,7 @@ struct HParams {
     int32_t TW, R, P, MT, box_rows;
     int32_t tiles_x, tiles_y, BN, kblocks, n_ntiles, total_tiles;
     int32_t nA, nB, a_bytes, a_tx, r_tx, b_bytes, tps;   // tps: taps per weight stage (stage = tps * b_bytes)
-    int32_t ngroups, res_blocks;
+    int32_t ngroups, res_blocks, stage_epi;   // stage_epi: epilogue stores go through a shared-memory transpose
     int8_t g_map[kMaxGroups], g_qy[kMaxGroups], g_qx[kMaxGroups], g_first[kMaxGroups + 1];
     int16_t t_shift[RGBD_MAX_TAPS];
     int8_t t_w[RGBD_MAX_TAPS];
@@ -207,11 +208,13 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float act_fn(float v, int act) {
-    if (act == RGBD_ACT_RELU) return v > 0.f ? v : 0.f;
-    if (act == RGBD_ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
-    return v;
+// Branch-free activation: max(v, slope * v) with slope 1 (none), 0 (ReLU) or 0.01 (LeakyReLU).  A runtime
+// switch on the activation kind compiles to three branches per element, which made the epilogue the
+// bottleneck of every small-K layer.
+__device__ __forceinline__ float act_slope(int act) {
+    return act == RGBD_ACT_RELU ? 0.f : (act == RGBD_ACT_LEAKY ? 0.01f : 1.f);
 }
+__device__ __forceinline__ float act_fn(float v, float slope) { return fmaxf(v, v * slope); }
 __device__ __forceinline__ void bilerp_axis(int dst, int in_size, int out_size, int &i0, int &i1, float &l1) {
     const float scale = (float)in_size / (float)out_size;
     float src = scale * ((float)dst + 0.5f) - 0.5f;
@@ -239,6 +242,14 @@ __device__ __forceinline__ uint4 pack8(const float *v) {
         w[i] = *reinterpret_cast<const uint32_t *>(&h);
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 // 16 consecutive bf16 channels of one pixel -> fp32 (vector path when 16-byte aligned and complete)
 __device__ __forceinline__ void load16_bf16(const __nv_bfloat16 *p, bool vec, int nvalid, float *v) {
@@ -328,6 +339,7 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
     // per-tap A descriptor offsets (row shift * 128 B >> 4), then the bias
     uint32_t *shift_s = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot + 16u - raw));
     float *bias_s = reinterpret_cast<float *>(smem_raw + (tmem_slot + 16u + 128u - raw));
+    const uint32_t stage_base = tmem_slot + 16u + 128u + 4u * (uint32_t)d.cout_pad;   // 16-byte aligned (cout_pad % 16 == 0)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -526,8 +538,8 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
         const int set = (warp - kFirstEpiWarp) >> 2;     // 0 / 1
         const int j = p.MT == 2 ? set : 0;               // accumulator (M tile) this warp drains
-        const int cfirst = p.MT == 2 ? 0 : set;          // MT == 1: the two warp sets split the 16-column chunks
-        const int cstep = p.MT == 2 ? 1 : 2;
+        const int cbfirst = p.MT == 2 ? 0 : set;         // MT == 1: the two warp sets split the 32-column blocks
+        const int cbstep = p.MT == 2 ? 1 : 2;
         const int pos = j * 128 + quad * 32 + lane;      // position inside the super-tile
         const int ty = pos / p.P, tx = pos - ty * p.P;
         TOut *y = reinterpret_cast<TOut *>(d.y);
@@ -541,9 +553,18 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
         const bool mul_vec = ((d.mul_cstride | d.mul_coff) & 7) == 0;
         // residual handled here only when it did not ride on the tensor core
         const bool res_direct = res != nullptr && kEpi != RGBD_EPI_BILERP && p.res_blocks == 0;
+        const float slope = act_slope(d.act);
+        // Coalesced stores: a thread owns one pixel row of the accumulator, so a direct 16-byte store touches
+        // 32 different 128-byte lines per warp instruction (one LSU wavefront each) — for the small-K layers
+        // that is the bottleneck.  Instead each warp transposes 32 rows x 32 channels through its private
+        // 2 KB tile (16-byte pieces XOR-swizzled by row pair) and stores 8 rows x 64 contiguous bytes per
+        // instruction.
+        const bool staged = p.stage_epi != 0 && sizeof(TOut) == 2 && kEpi != RGBD_EPI_BILERP && y_vec &&
+                            (y2 == nullptr || y2_vec) && (d.Cout & 7) == 0;
+        const uint32_t stg = stage_base + (uint32_t)(warp - kFirstEpiWarp) * 2048u;
         int li = 0;
         const bool tr = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == kFirstEpiWarp * 32;
-        long long w_full = 0;
+        long long w_full = 0, et[3] = {0, 0, 0};
         const long long t_begin = tr ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
             const TileCoord tc = tile_coord(p, tile);
@@ -572,7 +593,15 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                     pm[1] = q[1];
                 }
             };
-            if (kGate || res_direct) prefetch(cfirst);
+            const int nblk = (nchunks + 1) >> 1;
+            // the chunk this warp handles after chunk c (its blocks are cbfirst, cbfirst + cbstep, ...)
+            auto chunk_after = [&](int c) {
+                if ((c & 1) == 0 && c + 1 < nchunks) return c + 1;
+                const int nb = (c >> 1) + cbstep;
+                return nb < nblk ? 2 * nb : nchunks;
+            };
+            const int pix_code = valid ? (int)opix : -1;
+            if (kGate || res_direct) prefetch(2 * cbfirst);
             int by0 = 0, by1 = 0, bx0 = 0, bx1 = 0;
             float ly = 0.f, lx = 0.f;
             if (kEpi == RGBD_EPI_BILERP && valid) {
@@ -584,13 +613,14 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + j * 128);
             uint32_t r0[16], r1[16];
             auto process = [&](int c, const uint32_t *rv) {
+                const int cnext = chunk_after(c);
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rv[i]);
                 const int co = tc.co0 + c * 16;
                 const int nvalid = d.Cout - co;
                 uint4 cr[2] = {pr[0], pr[1]}, cm[2] = {pm[0], pm[1]};
-                if ((kGate || res_direct) && c + cstep < nchunks) prefetch(c + cstep);
+                if ((kGate || res_direct) && cnext < nchunks) prefetch(cnext);
                 if (valid && nvalid > 0) {
                     const bool full16 = nvalid >= 16;
                     {
@@ -633,7 +663,7 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                             for (int i = 0; i < 16; ++i) v[i] += r[i];
                         }
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = act_fn(v[i], d.act);
+                        for (int i = 0; i < 16; ++i) v[i] = act_fn(v[i], slope);
                     } else {  // RGBD_EPI_BILERP
                         const int64_t rbase = (int64_t)tc.n * d.res_H * d.res_W;
                         const int cc = d.res_coff + co;
@@ -646,23 +676,69 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                         for (int i = 0; i < 16; ++i) {
                             const float up = (1.f - ly) * ((1.f - lx) * a00[i] + lx * a01[i]) +
                                              ly * ((1.f - lx) * a10[i] + lx * a11[i]);
-                            v[i] = act_fn(v[i] + up, d.act);
+                            v[i] = act_fn(v[i] + up, slope);
                         }
                     }
-                    store16<TOut>(y + opix * d.y_cstride + d.y_coff + co, y_vec, nvalid, v);
-                    if (y2) store16<TOut>(y2 + opix * d.y2_cstride + d.y2_coff + co, y2_vec, nvalid, v);
+                    if (staged) {
+                        if constexpr (sizeof(TOut) == 2) {
+                            const uint32_t rowaddr = stg + (uint32_t)(lane * 64);
+                            const int f = (lane >> 1) & 3, h2 = (c & 1) * 2;
+                            sts128(rowaddr + (uint32_t)(((h2) ^ f) << 4), pack8(v));
+                            sts128(rowaddr + (uint32_t)(((h2 + 1) ^ f) << 4), pack8(v + 8));
+                        }
+                    } else {
+                        store16<TOut>(y + opix * d.y_cstride + d.y_coff + co, y_vec, nvalid, v);
+                        if (y2) store16<TOut>(y2 + opix * d.y2_cstride + d.y2_coff + co, y2_vec, nvalid, v);
+                    }
                 }
-                        };
-            if (cfirst < nchunks) tmem_ld16_issue(trow + (uint32_t)(cfirst * 16), r0);
-            for (int c = cfirst; c < nchunks; c += 2 * cstep) {
-                // the next chunk's accumulator columns travel while this chunk is processed
+            };
+            int cb = cbfirst;
+            if (cb < nblk) {
+                tmem_ld16_issue(trow + (uint32_t)(cb * 32), r0);
+                if (2 * cb + 1 < nchunks) tmem_ld16_issue(trow + (uint32_t)(cb * 32 + 16), r1);
+            }
+            for (; cb < nblk; cb += cbstep) {
+                const bool has1 = 2 * cb + 1 < nchunks;
+                const long long e0 = tr ? clock64() : 0;
                 tmem_ld_wait(r0);
-                if (c + cstep < nchunks) tmem_ld16_issue(trow + (uint32_t)((c + cstep) * 16), r1);
-                process(c, r0);
-                if (c + cstep < nchunks) {
+                const long long e1 = tr ? clock64() : 0;
+                process(2 * cb, r0);
+                if (has1) {
                     tmem_ld_wait(r1);
-                    if (c + 2 * cstep < nchunks) tmem_ld16_issue(trow + (uint32_t)((c + 2 * cstep) * 16), r0);
-                    process(c + cstep, r1);
+                    process(2 * cb + 1, r1);
+                }
+                const long long e2 = tr ? clock64() : 0;
+                // the next block's accumulator columns travel during the store phase
+                const int nb = cb + cbstep;
+                if (nb < nblk) {
+                    tmem_ld16_issue(trow + (uint32_t)(nb * 32), r0);
+                    if (2 * nb + 1 < nchunks) tmem_ld16_issue(trow + (uint32_t)(nb * 32 + 16), r1);
+                }
+                if (staged) {
+                    if constexpr (sizeof(TOut) == 2) {
+                        __syncwarp();
+                        const int q = lane & 3, rsub = lane >> 2;
+                        const int chb = tc.co0 + cb * 32 + q * 8;
+                        const bool pv = q * 8 < (has1 ? 32 : 16) && chb + 8 <= d.Cout;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = rsub + 8 * i;
+                            const int pc = __shfl_sync(0xffffffffu, pix_code, r);
+                            if (pv && pc >= 0) {
+                                const uint4 val = lds128(stg + (uint32_t)(r * 64 + ((q ^ ((r >> 1) & 3)) << 4)));
+                                *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(y) + (int64_t)pc * d.y_cstride + d.y_coff + chb) = val;
+                                if (y2)
+                                    *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(y2) + (int64_t)pc * d.y2_cstride + d.y2_coff + chb) = val;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (tr) {
+                    const long long e3 = clock64();
+                    et[0] += e1 - e0;
+                    et[1] += e2 - e1;
+                    et[2] += e3 - e2;
                 }
             }
             // all of this warp's tcgen05.ld have completed: hand the buffer back
@@ -673,6 +749,7 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
         if (tr) {
             p.dbg[7] = w_full;
             p.dbg[8] = clock64() - t_begin;
+            for (int i = 0; i < 3; ++i) p.dbg[9 + i] = et[i];
         }
     }
     tc_fence_before();
@@ -860,7 +937,9 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
             const double l2 = ((double)p.ngroups * p.kblocks * box_rows * P * 128.0 * cin_frac +
                                (double)d->ntaps * p.kblocks * p.b_bytes + (double)p.res_blocks * (R * P * 128.0 + p.b_bytes)) /
                               42.0;
-            const double per_tile = (mma > l2 ? mma : l2) + 0.15 * (mma < l2 ? mma : l2) + 1500.0;
+            // + a charge per image-row segment of the tile (TMA gathers and the epilogue's stores like long
+            // contiguous runs; this also breaks the tie for 1x1 filters towards wide tiles)
+            const double per_tile = (mma > l2 ? mma : l2) + 0.15 * (mma < l2 ? mma : l2) + 1500.0 + 40.0 * box_rows;
             const double cost = tiles * per_tile;
             if (best < 0 || cost < best) {
                 best = cost;
@@ -895,6 +974,12 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
         p.t_shift[i] = (int16_t)((tq_y[t] - p.g_qy[gi]) * p.P + (tq_x[t] - p.g_qx[gi]));
         p.t_w[i] = d->wtap[t];
     }
+    // small-K layers: the epilogue (not the MMAs) paces the kernel -> coalesce its stores through shared memory
+    // (measured on B200: once the activation is branch-free these layers are HBM-bound either way, so the
+    // transpose path is opt-in: RGBD_TC_STAGE=1)
+    static const bool env_stage = getenv("RGBD_TC_STAGE") != nullptr;
+    p.stage_epi = (env_stage && d->ntaps * p.kblocks <= 8 && d->y_dtype == RGBD_DT_BF16) ? 1 : 0;
+    const int kBudget = kRingBudget - (p.stage_epi ? kStageBytes : 0);
     // Weight stages hold up to 3 consecutive taps (<= 36 KB): one barrier round trip + commit per stage
     // costs an issuing thread ~600 cycles, which 4 MMAs per accumulator do not cover.
     int max_group_taps = 1;
@@ -908,9 +993,9 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     if (p.tps < 1) p.tps = 1;
     // ring depths: 2 A stages (more when affordable), at least 2 weight stages
     p.nA = 2;
-    while (p.tps > 1 && (kRingBudget - p.nA * p.a_bytes) / (p.tps * p.b_bytes) < 2) --p.tps;
+    while (p.tps > 1 && (kBudget - p.nA * p.a_bytes) / (p.tps * p.b_bytes) < 2) --p.tps;
     const int b_stage = p.tps * p.b_bytes;
-    p.nB = (kRingBudget - p.nA * p.a_bytes) / b_stage;
+    p.nB = (kBudget - p.nA * p.a_bytes) / b_stage;
     if (p.nB > kMaxB) p.nB = kMaxB;
     if (p.nB < 2) {
         rgbd_set_error("conv_tc: ring budget too small (a_bytes %d b_bytes %d)", p.a_bytes, p.b_bytes);
@@ -920,16 +1005,16 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     const int a_iters = p.kblocks * p.ngroups + p.res_blocks;
     const int nb_keep = p.tps > 1 ? 2 : 5;
     while (p.nA < kMaxA && p.nA < a_iters + 1 &&
-           (p.nA + 1) * p.a_bytes + (p.nB < nb_keep ? p.nB : nb_keep) * b_stage <= kRingBudget) {
+           (p.nA + 1) * p.a_bytes + (p.nB < nb_keep ? p.nB : nb_keep) * b_stage <= kBudget) {
         ++p.nA;
-        const int nb = (kRingBudget - p.nA * p.a_bytes) / b_stage;
+        const int nb = (kBudget - p.nA * p.a_bytes) / b_stage;
         if (nb < p.nB) p.nB = nb;
     }
     const long total = (long)d->N * p.tiles_x * p.tiles_y * p.n_ntiles;
     RGBD_CHECK_ARG(total < 2147483647L, "too many tiles");
     p.total_tiles = (int)total;
     pl->smem = (size_t)p.nA * p.a_bytes + (size_t)p.nB * p.tps * p.b_bytes + 1024 /*align*/ +
-               8 * (2 * kMaxA + 2 * kMaxB + 8) + 16 + 128 + 4 * (size_t)d->cout_pad + 64;
+               8 * (2 * kMaxA + 2 * kMaxB + 8) + 16 + 128 + 4 * (size_t)d->cout_pad + 64 + (p.stage_epi ? kStageBytes : 0);
     if (pl->smem < (size_t)kMinSmem) pl->smem = kMinSmem;
     static int num_sms = 0;
     if (num_sms == 0) {

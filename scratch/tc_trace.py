@@ -24,7 +24,7 @@ def run(name, mod, N, H, W, res=False, bytes_per_px=0):
     n = max(1, d[6])
     print(f"== {name}: {us:.0f} us, {fl/us/1e6:.0f} TFLOP/s | CTA0: {d[6]} tiles, mma thread total {d[5]} cyc ({d[5]/n:.0f}/tile): "
           f"wait tmem_empty {d[2]/n:.0f} a_full {d[3]/n:.0f} b_full {d[4]/n:.0f} | producers wait: a_empty {d[0]/n:.0f} b_empty {d[1]/n:.0f} "
-          f"| epilogue warp: total {d[8]/n:.0f}/tile, wait tmem_full {d[7]/n:.0f}", flush=True)
+          f"| epilogue warp: total {d[8]/n:.0f}/tile, wait tmem_full {d[7]/n:.0f} [ld wait {d[9]/n:.0f} process {d[10]/n:.0f} issue+store {d[11]/n:.0f}]", flush=True)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 run("1x1 96->192 + res @256x320", nn.Conv2d(96, 192, 1), B, 256, 320, res=True)
 run("1x1 192->96 @256x320", nn.Conv2d(192, 96, 1), B, 256, 320)

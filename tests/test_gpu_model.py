@@ -202,3 +202,31 @@ def test_nyuv2_size_roundtrip_properties():
     # dense conv flop count of the plan == the survey's algorithmic figure (721.2 + 785.1 GFLOP)
     assert abs(enc.flops / 1e9 - 721.2) < 1.0, enc.flops / 1e9
     assert abs(dec.flops / 1e9 - 785.1) < 1.0, dec.flops / 1e9
+
+
+def test_pipeline_matches_serial_calls():
+    """RoundTripPipeline (several compress + decompress jobs in flight on separate streams and launch plans)
+    returns, job by job, exactly what serial compress() / decompress() calls return."""
+    from gpu_utils import make_model
+    from rgbd_b200.pipeline import RoundTripPipeline
+    net, _ = make_model(rgbd_b200.ELIC_united, "mid", 0, precision="bf16")
+    jobs = []
+    for j in range(5):
+        rgb, depth = synthetic_pairs(2, 128, 128, seed=100 + j)
+        jobs.append((rgb.to(DEV), depth.to(DEV)))
+    want = []
+    for rgb, depth in jobs:
+        c = net.compress(rgb, depth)
+        r = net.decompress(c["r_strings"], c["d_strings"], c["shape"])
+        want.append((c, r["x_hat"]["r"].clone(), r["x_hat"]["d"].clone()))
+    seen = {}
+
+    def sink(j, slot, stream, x_r, x_d):
+        seen[j] = (x_r.clone(), x_d.clone())
+
+    res = RoundTripPipeline(net, 2).run(jobs, sink=sink, keep_last=5)
+    torch.cuda.synchronize()
+    assert [j for j, _, _ in res] == [0, 1, 2, 3, 4] and sorted(seen) == [0, 1, 2, 3, 4]
+    for j, c, _ in res:
+        assert c["r_strings"] == want[j][0]["r_strings"] and c["d_strings"] == want[j][0]["d_strings"], j
+        assert torch.equal(seen[j][0], want[j][1]) and torch.equal(seen[j][1], want[j][2]), j
