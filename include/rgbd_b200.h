@@ -90,9 +90,12 @@ typedef struct rgbd_conv_desc {
     int32_t act, epi;
     int32_t x_dtype, y_dtype; /* RGBD_DT_* */
     int32_t cout_pad;         /* packed weight row length (multiple of 16) */
+    int32_t w_image_stride;   /* tensor-core path: 0 = all images share w; else image n uses the weight
+                                 set that starts w_image_stride taps after image n-1's (per-image weights
+                                 produced by rgbd_scale_weights: the SE gate folded into the filter) */
     int8_t dy[RGBD_MAX_TAPS], dx[RGBD_MAX_TAPS];
     int8_t wtap[RGBD_MAX_TAPS];
-    int8_t _pad[5];
+    int8_t _pad[1];
 } rgbd_conv_desc;
 
 /* fp32-accumulate CUDA-core path: weights fp32 [ntaps_total][Cin][cout_pad]. Used for the
@@ -125,6 +128,12 @@ int rgbd_se_scale(const void *x, int32_t dtype, int32_t N, int32_t HW, int32_t C
 int rgbd_scale_channels(const void *x, void *y, int32_t dtype, const float *scale, int32_t N, int64_t HW,
                         int32_t C, int32_t x_cstride, int32_t x_coff, int32_t y_cstride, int32_t y_coff,
                         void *stream);
+/* w_out[n][t][co][ci] = bf16(w[t][co][ci] * scale[n][ci]) for ci < Cin (0 beyond): folds a per-image
+ * input-channel gate (SE_Block; EntropyParametersEX's `x + se(x)`, modules/transform/entropy.py:75) into
+ * per-image copies of a tensor-core filter [taps][cout_pad][cin_pad] instead of rescaling the (much
+ * larger) activation tensor; used with rgbd_conv_desc.w_image_stride = taps. */
+int rgbd_scale_weights(const float *w, const float *scale, void *w_out, int32_t N, int32_t taps,
+                       int32_t cout_pad, int32_t cin_pad, int32_t Cin, void *stream);
 /* F.max_pool2d(kernel 7, stride 3) of ESA (attention.py:88) */
 int rgbd_maxpool7s3(const void *x, void *y, int32_t dtype, int32_t N, int32_t H, int32_t W,
                     int32_t C, void *stream);
@@ -140,6 +149,10 @@ int rgbd_nhwc_to_nchw(const void *x, int32_t dtype, float *y, int32_t N, int32_t
  * async memset for the zero-initialised y_hat buffers (utils/ckbd.py:37-48 `torch.zeros_like`). */
 int rgbd_copy_view(const void *x, void *y, int32_t dtype, int64_t npix, int32_t C, int32_t x_cstride,
                    int32_t x_coff, int32_t y_cstride, int32_t y_coff, void *stream);
+/* fp32 NHWC view -> bf16 NHWC view (the latents y stay fp32 for the quantiser; the hyper-analysis
+ * h_a reads this bf16 copy on the tensor cores) */
+int rgbd_cast_view_bf16(const float *x, void *y, int64_t npix, int32_t C, int32_t x_cstride, int32_t x_coff,
+                        int32_t y_cstride, int32_t y_coff, void *stream);
 int rgbd_zero(void *p, int64_t bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------

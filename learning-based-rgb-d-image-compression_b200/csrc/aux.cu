@@ -139,6 +139,17 @@ __global__ void copy_view_kernel(const T *__restrict__ x, T *__restrict__ y, int
     }
 }
 
+__global__ void cast_view_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, int64_t npix, int C,
+                                      int xs, int xo, int ys, int yo) {
+    const int64_t total = npix * C;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = e / C;
+        const int c = (int)(e % C);
+        y[p * ys + yo + c] = __float2bfloat16_rn(x[p * xs + xo + c]);
+    }
+}
+
 template <typename T>
 __global__ void scale_channels_kernel(const T *__restrict__ x, T *__restrict__ y, const float *__restrict__ scale,
                                       int64_t pix_per_img, int64_t npix, int C, int xs, int xo, int ys, int yo) {
@@ -152,7 +163,43 @@ __global__ void scale_channels_kernel(const T *__restrict__ x, T *__restrict__ y
     }
 }
 
+// per-image filter copies with the input-channel gate folded in (8 input channels = 16 B per thread)
+__global__ void scale_weights_kernel(const float *__restrict__ w, const float *__restrict__ scale,
+                                     __nv_bfloat16 *__restrict__ out, int64_t per_image, int cin_pad, int Cin, int N) {
+    const int64_t groups = per_image / 8;
+    const int64_t total = groups * N;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(e / groups);
+        const int64_t g = e - (int64_t)n * groups;
+        const int ci = (int)((g * 8) % cin_pad);
+        const float4 a = reinterpret_cast<const float4 *>(w + g * 8)[0];
+        const float4 b = reinterpret_cast<const float4 *>(w + g * 8)[1];
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t packed[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float s0 = ci + 2 * i < Cin ? scale[(int64_t)n * Cin + ci + 2 * i] : 0.f;
+            const float s1 = ci + 2 * i + 1 < Cin ? scale[(int64_t)n * Cin + ci + 2 * i + 1] : 0.f;
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i] * s0, v[2 * i + 1] * s1);
+            packed[i] = *reinterpret_cast<const uint32_t *>(&h);
+        }
+        reinterpret_cast<uint4 *>(out + (int64_t)n * per_image + g * 8)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+}
+
 }  // namespace
+
+extern "C" int rgbd_scale_weights(const float *w, const float *scale, void *w_out, int32_t N, int32_t taps,
+                                  int32_t cout_pad, int32_t cin_pad, int32_t Cin, void *stream) {
+    RGBD_CHECK_ARG(w && scale && w_out, "null pointer");
+    RGBD_CHECK_ARG(N > 0 && taps > 0 && cout_pad > 0 && cin_pad > 0 && (cin_pad & 7) == 0 && Cin > 0 && Cin <= cin_pad, "dims");
+    RGBD_CHECK_ARG(((uintptr_t)w & 15) == 0 && ((uintptr_t)w_out & 15) == 0, "w / w_out must be 16-byte aligned");
+    const int64_t per_image = (int64_t)taps * cout_pad * cin_pad;
+    const int grid = rgbd_grid_for(per_image / 8 * N, 256);
+    scale_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, scale, (__nv_bfloat16 *)w_out, per_image, cin_pad, Cin, N);
+    RGBD_LAUNCH_CHECK();
+    return RGBD_OK;
+}
 
 extern "C" int rgbd_scale_channels(const void *x, void *y, int32_t dtype, const float *scale, int32_t N, int64_t HW,
                                    int32_t C, int32_t x_cstride, int32_t x_coff, int32_t y_cstride, int32_t y_coff,
@@ -184,6 +231,16 @@ extern "C" int rgbd_copy_view(const void *x, void *y, int32_t dtype, int64_t npi
     else
         copy_view_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, npix, C,
                                                                x_cstride, x_coff, y_cstride, y_coff);
+    RGBD_LAUNCH_CHECK();
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_cast_view_bf16(const float *x, void *y, int64_t npix, int32_t C, int32_t x_cstride, int32_t x_coff,
+                                   int32_t y_cstride, int32_t y_coff, void *stream) {
+    RGBD_CHECK_ARG(x && y, "null pointer");
+    RGBD_CHECK_ARG(npix > 0 && C > 0, "dims");
+    cast_view_bf16_kernel<<<rgbd_grid_for(npix * C, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, (__nv_bfloat16 *)y, npix, C, x_cstride, x_coff, y_cstride, y_coff);
     RGBD_LAUNCH_CHECK();
     return RGBD_OK;
 }

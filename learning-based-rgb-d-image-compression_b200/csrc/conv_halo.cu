@@ -415,7 +415,7 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                             mbar_expect_tx(b_full(s), (uint32_t)(n * p.b_bytes));
                             for (int tt = 0; tt < n; ++tt)
                                 tma_load_3d(b_base + (uint32_t)s * b_stage + (uint32_t)(tt * p.b_bytes), &p.bmap, b_full(s),
-                                            kb * kBlockK, tc.co0, p.t_w[t + tt]);
+                                            kb * kBlockK, tc.co0, p.t_w[t + tt] + tc.n * d.w_image_stride);
                         }
                     }
                 }
@@ -846,6 +846,8 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     RGBD_CHECK_ARG(cin_pad >= d->Cin && (cin_pad % kBlockK) == 0, "cin_pad must be a multiple of 64 >= Cin");
     RGBD_CHECK_ARG(d->i_step == 1 || d->i_step == 2, "i_step must be 1 or 2");
     RGBD_CHECK_ARG(d->cout_pad <= kMaxBias, "cout_pad too large");
+    for (int t = 0; t < d->ntaps; ++t)
+        RGBD_CHECK_ARG(d->w_image_stride == 0 || d->w_image_stride > d->wtap[t], "w_image_stride must cover every tap");
     RGBD_CHECK_ARG((int64_t)d->N * d->Ho * d->Wo < 2147483647LL, "too many output pixels");
 
     rgbd_conv_tc_plan *pl = new (std::nothrow) rgbd_conv_tc_plan();
@@ -1049,7 +1051,9 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     int max_tap = 0;
     for (int t = 0; t < d->ntaps; ++t) max_tap = d->wtap[t] > max_tap ? d->wtap[t] : max_tap;
     {
-        cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)d->cout_pad, (cuuint64_t)(max_tap + 1)};
+        // per-image weight sets (w_image_stride taps apart) are further slices of the same tap dimension
+        cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)d->cout_pad,
+                              (cuuint64_t)(max_tap + 1) + (cuuint64_t)d->w_image_stride * (cuuint64_t)(d->N - 1)};
         cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * d->cout_pad * 2};
         cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)p.BN, 1};
         rc = encode_map(&p.bmap, d->w, 3, dims, strides, box);

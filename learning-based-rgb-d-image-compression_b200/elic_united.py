@@ -292,7 +292,15 @@ class ELIC_united(nn.Module):
     def _h_a(self, b, y_r, y_d):
         outs = []
         for seq, y in ((self.h_a.rgb_reduction, y_r), (self.h_a.depth_reduction, y_d)):
-            t1 = b.conv(self._pc(seq[0]), y, act=RELU)
+            if b.tensor_cores and y.dtype == torch.float32:
+                # y stays fp32 for the quantiser; h_a reads a bf16 copy on the tensor cores
+                y16 = b.alloc(y.N, y.H, y.W, y.C, torch.bfloat16)
+                b.op("rgbd_cast_view_bf16", y.ptr(), y16.ptr(), y.N * y.H * y.W, y.C, y.cstride, y.coff, y16.cstride,
+                     y16.coff)
+                t1 = b.conv(self._pc(seq[0]), y16, act=RELU)
+                b.release(y16)
+            else:
+                t1 = b.conv(self._pc(seq[0]), y, act=RELU)
             t2 = b.conv(self._pc(seq[2]), t1, act=RELU)
             z = b.conv(self._pc(seq[4]), t2, out_dtype=torch.float32)
             b.release(t1, t2)
@@ -409,6 +417,13 @@ class ELIC_united(nn.Module):
         params into y_hat at the parity sites (quantise in the encoder, rANS-decode in the decoder,
         ste + likelihood in forward).  ctx_rgb is the rgb-only context buffer of the R2D variant."""
         cross = self.cross
+        if b.tensor_cores:
+            # one scratch buffer for the per-image SE-folded 1x1 filters of every EntropyParametersEX stage
+            eps = [m for lst in (self.rgb_entropy_parameters_anchor, self.depth_entropy_parameters_anchor,
+                                 self.rgb_entropy_parameters_nonanchor, self.depth_entropy_parameters_nonanchor)
+                   for m in lst]
+            b.reserve_wscratch(ctx.N * max((m.fusion[0].out_channels + 15) // 16 * 16 *
+                                           ((m.fusion[0].in_channels + 63) // 64 * 64) for m in eps))
         for idx, g in enumerate(self.slice_ch):
             coff = sum(self.slice_ch[:idx])
             o, perms, o_r = self._ctx_layout(idx)

@@ -79,6 +79,19 @@ class PackedConv:
         self.w32 = packed.contiguous()
         self.bias = None if mod.bias is None else mod.bias.detach().to(device=device, dtype=torch.float32).contiguous()
         self._wtc = None
+        self._wtc32 = None
+
+    @property
+    def wtc32(self):
+        """fp32 master copy in the tensor-core layout [taps][cout_pad][cin_pad]: the source of the per-image
+        SE-folded filters (rgbd_scale_weights rounds w * scale to bf16 once, from fp32)."""
+        if self._wtc32 is None:
+            T, cin, cp = self.w32.shape
+            self.cin_pad = (cin + 63) // 64 * 64
+            w = torch.zeros(T, cp, self.cin_pad, device=self.w32.device, dtype=torch.float32)
+            w[:, :, :cin] = self.w32.permute(0, 2, 1)
+            self._wtc32 = w.contiguous()
+        return self._wtc32
 
     @property
     def wtc(self):
@@ -167,6 +180,7 @@ class Builder:
         self.device = device
         self.act_dtype = act_dtype
         self.prog = Program(device)
+        self._wscratch = None   # per-image SE-folded filters of the layer being run (shared by all layers)
         # tcgen05 path: bf16 activations only
         self.tensor_cores = (act_dtype == torch.bfloat16) if tensor_cores is None else tensor_cores
 
@@ -193,6 +207,11 @@ class Builder:
         self.prog.bytes += t.numel() * t.element_size()
         self.prog.keep.append(t)
         return t
+
+    def reserve_wscratch(self, elems):
+        if self._wscratch is None or self._wscratch.numel() < elems:
+            self._wscratch = self.raw((int(elems),), torch.bfloat16)
+        return self._wscratch
 
     # ---- ops ----
     def op(self, name, *args):
@@ -221,6 +240,19 @@ class Builder:
         # channel block beyond Cin, so a tap costs one K=16 MMA
         use_tc = self.tensor_cores and x.dtype == torch.bfloat16 and x.cstride % 8 == 0 and x.coff % 8 == 0
         scaled = None
+        w_folded = None
+        if use_tc and in_scale is not None:
+            T, _, cp = pc.w32.shape
+            w_elems = T * cp * ((pc.Cin + 63) // 64 * 64)
+            if w_elems < x.H * x.W * x.C:
+                # the gate is per (image, input channel): fold it into per-image copies of the filter, which is
+                # smaller than the activation tensor (the 1x1 of EntropyParametersEX: <= 2816 x 480 vs 1280 px)
+                src = pc.wtc32
+                w_folded = self.reserve_wscratch(x.N * w_elems)
+                self.op("rgbd_scale_weights", src.data_ptr(), in_scale.data_ptr(), w_folded.data_ptr(), x.N, T, cp,
+                        pc.cin_pad, pc.Cin)
+                self.prog.keep.append(src)
+                in_scale = None
         if use_tc and in_scale is not None:
             # the TMA-fed A operand never passes through registers: apply the SE gate in a separate pass
             scaled = self.alloc(x.N, x.H, x.W, x.C, x.dtype)
@@ -261,6 +293,9 @@ class Builder:
             self.prog.keep.append(d)
             if use_tc:
                 d.w = pc.wtc.data_ptr()
+                if w_folded is not None:
+                    d.w = w_folded.data_ptr()
+                    d.w_image_stride = pc.w32.shape[0]
                 handle = C.c_void_p()
                 L.check(L.load().rgbd_conv_tc_plan_create(C.byref(d), pc.cin_pad, C.byref(handle)),
                         "rgbd_conv_tc_plan_create")

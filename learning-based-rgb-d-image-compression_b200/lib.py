@@ -35,9 +35,9 @@ class ConvDesc(C.Structure):
         ("mul_cstride", C.c_int32), ("mul_coff", C.c_int32),
         ("act", C.c_int32), ("epi", C.c_int32),
         ("x_dtype", C.c_int32), ("y_dtype", C.c_int32),
-        ("cout_pad", C.c_int32),
+        ("cout_pad", C.c_int32), ("w_image_stride", C.c_int32),
         ("dy", C.c_int8 * MAX_TAPS), ("dx", C.c_int8 * MAX_TAPS), ("wtap", C.c_int8 * MAX_TAPS),
-        ("_pad", C.c_int8 * 5),
+        ("_pad", C.c_int8 * 1),
     ]
 
 
@@ -61,7 +61,9 @@ _PROTOS = {
     "rgbd_nchw_to_nhwc": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_nhwc_to_nchw": [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_scale_channels": [_vp, _vp, _i32, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
+    "rgbd_scale_weights": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_copy_view": [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
+    "rgbd_cast_view_bf16": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_zero": [_vp, _i64, _vp],
     "rgbd_ckbd_quantize_index": [_vp, _i32, _i32, _vp, _vp, _i32, _f32, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
                                  _i64, _i64, _vp, _i32, _i32, _i32, _vp],

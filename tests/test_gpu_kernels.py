@@ -372,6 +372,18 @@ def test_conv_tc_epilogues():
     scale = torch.rand(2, 96) + 0.5
     want = bf16_ref(mod, (x.bfloat16().float() * scale[:, :, None, None]))
     assert rel_err(run_conv_tc(mod, x, in_scale=scale), want) < 1e-2
+    # larger map: the gate is folded into per-image filter copies instead (rgbd_scale_weights, one bf16
+    # rounding of w * scale from fp32)
+    xl = torch.randn(3, 96, 32, 40)
+    sl = torch.rand(3, 96) + 0.5
+    m_ref = nn.Conv2d(96, 192, 1).eval()
+    outs = []
+    for n in range(3):
+        with torch.no_grad():
+            m_ref.weight.copy_((mod.weight * sl[n][None, :, None, None]).bfloat16().float())
+            m_ref.bias.copy_(mod.bias)
+            outs.append(m_ref(xl[n:n + 1].bfloat16().float()))
+    assert rel_err(run_conv_tc(mod, xl, in_scale=sl), torch.cat(outs)) < 1e-3
     mod2 = nn.Conv2d(48, 48, 1).eval()
     x2 = torch.randn(2, 48, 37, 45)
     for small in ((2, 48, 5, 7), (2, 48, 11, 13)):
