@@ -5,7 +5,9 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, torch.nn as nn
 DEV = "cuda:0"
 dbg = torch.zeros(16, dtype=torch.int64, device=DEV)
-os.environ["RGBD_TC_TRACE"] = str(dbg.data_ptr())
+NCU = os.environ.get("RGBD_NCU") == "1"   # under ncu: no tracing, one launch per layer
+if not NCU:
+    os.environ["RGBD_TC_TRACE"] = str(dbg.data_ptr())
 from rgbd_b200.engine import Builder, PackedConv, View
 def run(name, mod, N, H, W, res=False, bytes_per_px=0):
     b = Builder(torch.device(DEV), torch.bfloat16, tensor_cores=True)
@@ -14,7 +16,7 @@ def run(name, mod, N, H, W, res=False, bytes_per_px=0):
     if res:
         r = b.alloc(N, H // mod.stride[0], W // mod.stride[0], mod.out_channels); r.buf.normal_()
     out = b.conv(PackedConv(mod, torch.device(DEV)), x, res=r)
-    for _ in range(3): b.prog.run()
+    for _ in range(0 if NCU else 3): b.prog.run()
     torch.cuda.synchronize(); dbg.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); b.prog.run(); e1.record(); torch.cuda.synchronize()
