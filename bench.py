@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU per step (default: by precision)")
     ap.add_argument("--precision", default=os.environ.get("RGBD_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--slots", type=int, default=6, help="batches in flight per GPU (own program + CUDA stream each)")
+    ap.add_argument("--slots", type=int, default=8, help="batches in flight per GPU (own program + CUDA stream each)")
     ap.add_argument("--graphs", type=int, default=0, help="replay each slot's launch list as a CUDA graph")
     ap.add_argument("--preset", default="realistic")
     ap.add_argument("--height", type=int, default=480)
@@ -277,6 +277,7 @@ def run_b200(args):
                                    f"{args.height}x{args.width} (padded {Hp}x{Wp}), preset {args.preset}, "
                                    f"weights calibrated random-init", "pairs_per_gpu": S * B, "batch": B, "slots_in_flight": S, "schedule": "pipelined: S compress + S decompress jobs in flight (rgbd_b200.pipeline)", "precision": args.precision, "cuda_graphs": bool(args.graphs),
                        "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
+                       "hbm_peak_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
                        "parallelism": f"dp{world} (images sharded, no data-path collective)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e / K},

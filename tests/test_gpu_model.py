@@ -230,3 +230,34 @@ def test_pipeline_matches_serial_calls():
     for j, c, _ in res:
         assert c["r_strings"] == want[j][0]["r_strings"] and c["d_strings"] == want[j][0]["d_strings"], j
         assert torch.equal(seen[j][0], want[j][1]) and torch.equal(seen[j][1], want[j][2]), j
+
+
+@pytest.mark.parametrize("cls_name,H,W", [("ELIC_united_R2D", 530, 730), ("ELIC_united", 1080, 1920)])
+def test_other_baseline_shapes_roundtrip(cls_name, H, W):
+    """BASELINE configs[3] / [4]: SUN RGB-D-shaped 530x730 through ELIC_united_R2D (padded to 576x768) and a
+    1080x1920 pair (padded to 1088x1920) in the bf16 tensor-core mode.  Size-independent properties: the
+    decoder reproduces every encoder symbol, every stream is byte-identical to the oracle coder on the
+    GPU's symbols, compress is idempotent, the reconstruction is finite and in [0, 1]."""
+    from gpu_utils import make_model
+    cls = getattr(rgbd_b200, cls_name)
+    net, sd = make_model(cls, "realistic", 0, precision="bf16")
+    orc = OracleCodec(sd, cross=cls_name == "ELIC_united")
+    rgb, depth = synthetic_pairs(1, H, W, seed=9)
+    rgb, depth = pad_to_multiple(rgb), pad_to_multiple(depth)
+    Hp, Wp = rgb.shape[-2:]
+    assert Hp % 64 == 0 and Wp % 64 == 0
+    out = net.compress(rgb.to(DEV), depth.to(DEV))
+    assert tuple(out["shape"]) == (Hp // 64, Wp // 64)
+    _check_bytes_against_oracle_coder(net, orc, out, 1, Hp, Wp)
+    enc = net._program("encoder", 1, Hp, Wp)
+    assert enc.io["ny"] == 320 * (Hp // 16) * (Wp // 16)
+    sym = {k: enc.io["st"][k]["ysym"].clone() for k in ("r", "d")}
+    rec = net.decompress(out["r_strings"], out["d_strings"], out["shape"])
+    dec = net._program("decoder", 1, Hp // 64, Wp // 64)
+    for k in ("r", "d"):
+        assert torch.equal(dec.io["st"][k]["ysym"], sym[k]), k
+    for m, c in (("r", 3), ("d", 1)):
+        x = rec["x_hat"][m]
+        assert x.shape == (1, c, Hp, Wp) and torch.isfinite(x).all() and x.min() >= 0 and x.max() <= 1
+    out2 = net.compress(rgb.to(DEV), depth.to(DEV))
+    assert out2["r_strings"] == out["r_strings"] and out2["d_strings"] == out["d_strings"]
