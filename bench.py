@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU per step (default: by precision)")
     ap.add_argument("--precision", default=os.environ.get("RGBD_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--slots", type=int, default=8, help="batches in flight per GPU (own program + CUDA stream each)")
-    ap.add_argument("--graphs", type=int, default=0, help="replay each slot's launch list as a CUDA graph")
+    ap.add_argument("--graphs", type=int, default=1, help="replay each slot's launch list as a CUDA graph")
     ap.add_argument("--preset", default="realistic")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)

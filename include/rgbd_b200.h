@@ -53,6 +53,8 @@ const char *rgbd_last_error(void);
 int rgbd_abi_version(void);
 /* number of kernels this library has launched since the last reset (bench bookkeeping) */
 int64_t rgbd_launch_count(int reset);
+/* adds n to that counter: a CUDA-graph replay of a captured launch list reports its kernel nodes here */
+void rgbd_count_launch(int n);
 
 /* ------------------------------------------------------------------------------------------
  * Convolution family (implicit GEMM over NHWC pixels).

@@ -314,11 +314,11 @@ __device__ __forceinline__ TileCoord tile_coord(const HParams &p, int tile) {
     return t;
 }
 
-// Register cap: 384 threads x 152 registers leave >= 7 K registers (and the ring budget leaves >= 60 KB of
+// Register cap: 384 threads x 144 registers leave 10 K registers (and the ring budget leaves >= 60 KB of
 // shared memory) on the SM, so that a rANS coder block (64 threads x 48 registers, 57 + 4 KB) can be
 // co-resident — the serial rANS chains of the other pipeline slots must not fence SMs off from the convs.
 template <typename TOut, int kEpi>
-__global__ void __maxnreg__(152)
+__global__ void __maxnreg__(144)
 conv_halo_kernel(const __grid_constant__ HParams p) {
     constexpr bool kGate = kEpi == RGBD_EPI_GATE;
     extern __shared__ uint8_t smem_raw[];

@@ -137,6 +137,7 @@ class Program:
         self.bytes = 0
         self.io = {}
         self.graph = None
+        self.graph_launches = 0
         self.flops = 0      # dense conv flops of one run (MAC * 2)
         self.tc_plans = []  # rgbd_conv_tc_plan handles owned by this program
         self.n_tc = 0
@@ -155,6 +156,7 @@ class Program:
             if self.graph is None:
                 self._capture()
             self.graph.replay()
+            L.load().rgbd_count_launch(self.graph_launches)   # the replayed kernel nodes
             return
         sp = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         for op in self.ops:
@@ -168,10 +170,14 @@ class Program:
             self.run(False)
         torch.cuda.current_stream(self.device).wait_stream(s)
         g = torch.cuda.CUDAGraph()
+        lib = L.load()
+        before = lib.rgbd_launch_count(0)
         with torch.cuda.graph(g):
             sp = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             for op in self.ops:
                 op(sp)
+        self.graph_launches = int(lib.rgbd_launch_count(0) - before)   # kernel nodes in the graph
+        lib.rgbd_count_launch(-self.graph_launches)                    # capture itself launched nothing
         self.graph = g
 
 

@@ -81,7 +81,7 @@ _PROTOS = {
 }
 
 # every symbol include/rgbd_b200.h declares (checked by tests/test_abi.py)
-EXPORTS = sorted(list(_PROTOS.keys()) + ["rgbd_last_error", "rgbd_abi_version", "rgbd_launch_count",
+EXPORTS = sorted(list(_PROTOS.keys()) + ["rgbd_last_error", "rgbd_abi_version", "rgbd_launch_count", "rgbd_count_launch",
                                           "rgbd_conv_tc_plan_destroy"])
 EXPORTS.remove("rgbd_conv_validate")
 
@@ -107,6 +107,8 @@ def load():
     lib.rgbd_abi_version.restype = C.c_int
     lib.rgbd_launch_count.restype = C.c_int64
     lib.rgbd_launch_count.argtypes = [C.c_int]
+    lib.rgbd_count_launch.restype = None
+    lib.rgbd_count_launch.argtypes = [C.c_int]
     lib.rgbd_conv_tc_plan_destroy.restype = None
     lib.rgbd_conv_tc_plan_destroy.argtypes = [_vp]
     _lib = lib
