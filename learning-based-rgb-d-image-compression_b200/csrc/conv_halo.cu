@@ -52,11 +52,12 @@ constexpr int kMaxBias = 1024;
 
 struct HParams {
     CUtensorMap amap[4];
-    CUtensorMap bmap, rmap, emap;
+    CUtensorMap bmap, rmap, emap, mmap;   // mmap: gate operand (RGBD_EPI_GATE `mul`) tiles
     rgbd_conv_desc d;
     int32_t TW, R, P, MT, box_rows;
     int32_t tiles_x, tiles_y, BN, kblocks, n_ntiles, total_tiles;
     int32_t nA, nB, a_bytes, a_tx, r_tx, b_bytes, tps;   // tps: taps per weight stage (stage = tps * b_bytes)
+    int32_t mul_blocks, mul_bytes;   // gate operand staged by TMA: 64-channel blocks per N tile, bytes per block (0: epilogue loads it)
     int32_t ngroups, res_blocks, stage_epi;   // stage_epi: epilogue stores go through a shared-memory transpose
     int8_t g_map[kMaxGroups], g_qy[kMaxGroups], g_qx[kMaxGroups], g_first[kMaxGroups + 1];
     int16_t t_shift[RGBD_MAX_TAPS];
@@ -215,6 +216,11 @@ __device__ __forceinline__ float act_slope(int act) {
     return act == RGBD_ACT_RELU ? 0.f : (act == RGBD_ACT_LEAKY ? 0.01f : 1.f);
 }
 __device__ __forceinline__ float act_fn(float v, float slope) { return fmaxf(v, v * slope); }
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void bilerp_axis(int dst, int in_size, int out_size, int &i0, int &i1, float &l1) {
     const float scale = (float)in_size / (float)out_size;
     float src = scale * ((float)dst + 0.5f) - 0.5f;
@@ -337,12 +343,16 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
     auto b_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxA + kMaxB + s); };
     auto tmem_full_bar = [&](int a, int j) { return bar_base + 8u * (uint32_t)(2 * kMaxA + 2 * kMaxB + 2 * a + j); };
     auto tmem_empty_bar = [&](int a, int j) { return bar_base + 8u * (uint32_t)(2 * kMaxA + 2 * kMaxB + 4 + 2 * a + j); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxA + 2 * kMaxB + 8);
+    auto mul_full = [&](int b) { return bar_base + 8u * (uint32_t)(2 * kMaxA + 2 * kMaxB + 8 + b); };
+    auto mul_empty = [&](int b) { return bar_base + 8u * (uint32_t)(2 * kMaxA + 2 * kMaxB + 10 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxA + 2 * kMaxB + 12);
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
     // per-tap A descriptor offsets (row shift * 128 B >> 4), then the bias
     uint32_t *shift_s = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot + 16u - raw));
     float *bias_s = reinterpret_cast<float *>(smem_raw + (tmem_slot + 16u + 128u - raw));
     const uint32_t stage_base = tmem_slot + 16u + 128u + 4u * (uint32_t)d.cout_pad;   // 16-byte aligned (cout_pad % 16 == 0)
+    // gate operand tiles (1024-byte aligned: the TMA 128-byte swizzle is a function of the address)
+    const uint32_t mul_base = (stage_base + (p.stage_epi ? (uint32_t)kStageBytes : 0u) + 1023u) & ~1023u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -360,6 +370,10 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                 mbar_init(tmem_full_bar(a, j), 1);
                 mbar_init(tmem_empty_bar(a, j), (uint32_t)(kEpiWarps / p.MT));
             }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(mul_full(b), 1);
+            mbar_init(mul_empty(b), kEpiWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -376,6 +390,7 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
         // =========================== A producer (halo tiles, residual tiles) ===========================
         if (lane == 0) {
             RingPos ra = {0, 0};
+            int mli = 0;
             const bool tr = p.dbg != nullptr && blockIdx.x == 0;
             long long w_empty = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -396,6 +411,18 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                     mbar_expect_tx(a_full(s), (uint32_t)p.r_tx);
                     tma_load_4d(a_base + (uint32_t)(s * p.a_bytes), &p.rmap, a_full(s), tc.co0 + jb * kBlockK, tc.ox0,
                                 tc.oy0, tc.n);
+                }
+                if (p.mul_blocks) {
+                    // gate operand of this tile: lands while the MMAs run; the epilogue reads it from shared memory
+                    // (double buffered: tile i + 1's operand travels while the epilogue works on tile i)
+                    const int nb = (tc.bn + 63) >> 6;
+                    const int mb = mli & 1;
+                    mbar_wait(mul_empty(mb), (uint32_t)((mli >> 1) & 1) ^ 1u);
+                    mbar_expect_tx(mul_full(mb), (uint32_t)(nb * p.r_tx));
+                    for (int jb = 0; jb < nb; ++jb)
+                        tma_load_4d(mul_base + (uint32_t)((mb * p.mul_blocks + jb) * p.mul_bytes), &p.mmap, mul_full(mb),
+                                    tc.co0 + jb * kBlockK, tc.ox0, tc.oy0, tc.n);
+                    ++mli;
                 }
             }
             if (tr) p.dbg[0] = w_empty;
@@ -557,6 +584,7 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
         // residual handled here only when it did not ride on the tensor core
         const bool res_direct = res != nullptr && kEpi != RGBD_EPI_BILERP && p.res_blocks == 0;
         const float slope = act_slope(d.act);
+        const bool mul_staged = kGate && p.mul_blocks != 0;
         // Coalesced stores: a thread owns one pixel row of the accumulator, so a direct 16-byte store touches
         // 32 different 128-byte lines per warp instruction (one LSU wavefront each) — for the small-K layers
         // that is the bottleneck.  Instead each warp transposes 32 rows x 32 channels through its private
@@ -590,7 +618,7 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                     pr[0] = q[0];
                     pr[1] = q[1];
                 }
-                if (kGate && on && mul_vec) {
+                if (kGate && on && mul_vec && !mul_staged) {
                     const uint4 *q = reinterpret_cast<const uint4 *>(mul + opix * d.mul_cstride + d.mul_coff + co);
                     pm[0] = q[0];
                     pm[1] = q[1];
@@ -611,6 +639,7 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                 bilerp_axis(oy, d.res_H, d.Ho, by0, by1, ly);
                 bilerp_axis(ox, d.res_W, d.Wo, bx0, bx1, lx);
             }
+            if (mul_staged) mbar_wait(mul_full(li & 1), (uint32_t)((li >> 1) & 1));
             mbar_wait_t(tmem_full_bar(acc, j), use & 1u, tr, w_full);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + j * 128);
@@ -647,15 +676,30 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                         }
                     }
                     if (kGate) {
-                        float m[16];
-                        if (mul_vec && full16) {
-                            unpack8(cm[0], m);
-                            unpack8(cm[1], m + 8);
+                        // sigmoid(v) = 0.5 * tanh(0.5 v) + 0.5: one MUFU op per element instead of ex2 + rcp
+                        uint4 q0, q1;
+                        if (mul_staged) {
+                            // this thread's pixel row of the TMA-staged tile: 16-byte chunk q lives at q ^ (row & 7)
+                            const uint32_t rowa = mul_base + (uint32_t)(((li & 1) * p.mul_blocks + (c >> 2)) * p.mul_bytes + pos * 128);
+                            const int qq = (c & 3) * 2, sw = pos & 7;
+                            q0 = lds128(rowa + (uint32_t)(((qq) ^ sw) << 4));
+                            q1 = lds128(rowa + (uint32_t)(((qq + 1) ^ sw) << 4));
+                        } else if (mul_vec && full16) {
+                            q0 = cm[0];
+                            q1 = cm[1];
                         } else {
+                            float m[16];
                             load16_bf16(mul + opix * d.mul_cstride + d.mul_coff + co, false, nvalid, m);
+                            q0 = pack8(m);
+                            q1 = pack8(m + 8);
                         }
+                        float m[8];
+                        unpack8(q0, m);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = m[i] * __fdividef(1.0f, 1.0f + __expf(-v[i]));
+                        for (int i = 0; i < 8; ++i) v[i] = m[i] * fmaf(tanh_approx(0.5f * v[i]), 0.5f, 0.5f);
+                        unpack8(q1, m);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[8 + i] = m[i] * fmaf(tanh_approx(0.5f * v[8 + i]), 0.5f, 0.5f);
                         if (res_direct) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] += r[i];
@@ -695,59 +739,69 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                     }
                 }
             };
-            int cb = cbfirst;
-            if (cb < nblk) {
-                tmem_ld16_issue(trow + (uint32_t)(cb * 32), r0);
-                if (2 * cb + 1 < nchunks) tmem_ld16_issue(trow + (uint32_t)(cb * 32 + 16), r1);
-            }
-            for (; cb < nblk; cb += cbstep) {
-                const bool has1 = 2 * cb + 1 < nchunks;
-                const long long e0 = tr ? clock64() : 0;
-                tmem_ld_wait(r0);
-                const long long e1 = tr ? clock64() : 0;
-                process(2 * cb, r0);
-                if (has1) {
-                    tmem_ld_wait(r1);
-                    process(2 * cb + 1, r1);
+            if constexpr (kGate || kEpi == RGBD_EPI_BILERP) {
+                // these epilogues keep their operands in registers too: one accumulator chunk in flight (no spills)
+                for (int c = 2 * cbfirst; c < nchunks; c = chunk_after(c)) {
+                    tmem_ld16_issue(trow + (uint32_t)(c * 16), r0);
+                    tmem_ld_wait(r0);
+                    process(c, r0);
                 }
-                const long long e2 = tr ? clock64() : 0;
-                // the next block's accumulator columns travel during the store phase
-                const int nb = cb + cbstep;
-                if (nb < nblk) {
-                    tmem_ld16_issue(trow + (uint32_t)(nb * 32), r0);
-                    if (2 * nb + 1 < nchunks) tmem_ld16_issue(trow + (uint32_t)(nb * 32 + 16), r1);
+            } else {
+                int cb = cbfirst;
+                if (cb < nblk) {
+                    tmem_ld16_issue(trow + (uint32_t)(cb * 32), r0);
+                    if (2 * cb + 1 < nchunks) tmem_ld16_issue(trow + (uint32_t)(cb * 32 + 16), r1);
                 }
-                if (staged) {
-                    if constexpr (sizeof(TOut) == 2) {
-                        __syncwarp();
-                        const int q = lane & 3, rsub = lane >> 2;
-                        const int chb = tc.co0 + cb * 32 + q * 8;
-                        const bool pv = q * 8 < (has1 ? 32 : 16) && chb + 8 <= d.Cout;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int r = rsub + 8 * i;
-                            const int pc = __shfl_sync(0xffffffffu, pix_code, r);
-                            if (pv && pc >= 0) {
-                                const uint4 val = lds128(stg + (uint32_t)(r * 64 + ((q ^ ((r >> 1) & 3)) << 4)));
-                                *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(y) + (int64_t)pc * d.y_cstride + d.y_coff + chb) = val;
-                                if (y2)
-                                    *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(y2) + (int64_t)pc * d.y2_cstride + d.y2_coff + chb) = val;
-                            }
-                        }
-                        __syncwarp();
+                for (; cb < nblk; cb += cbstep) {
+                    const bool has1 = 2 * cb + 1 < nchunks;
+                    const long long e0 = tr ? clock64() : 0;
+                    tmem_ld_wait(r0);
+                    const long long e1 = tr ? clock64() : 0;
+                    process(2 * cb, r0);
+                    if (has1) {
+                        tmem_ld_wait(r1);
+                        process(2 * cb + 1, r1);
                     }
-                }
-                if (tr) {
-                    const long long e3 = clock64();
-                    et[0] += e1 - e0;
-                    et[1] += e2 - e1;
-                    et[2] += e3 - e2;
+                    const long long e2 = tr ? clock64() : 0;
+                    // the next block's accumulator columns travel during the store phase
+                    const int nb = cb + cbstep;
+                    if (nb < nblk) {
+                        tmem_ld16_issue(trow + (uint32_t)(nb * 32), r0);
+                        if (2 * nb + 1 < nchunks) tmem_ld16_issue(trow + (uint32_t)(nb * 32 + 16), r1);
+                    }
+                    if (staged) {
+                        if constexpr (sizeof(TOut) == 2) {
+                            __syncwarp();
+                            const int q = lane & 3, rsub = lane >> 2;
+                            const int chb = tc.co0 + cb * 32 + q * 8;
+                            const bool pv = q * 8 < (has1 ? 32 : 16) && chb + 8 <= d.Cout;
+    #pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int r = rsub + 8 * i;
+                                const int pc = __shfl_sync(0xffffffffu, pix_code, r);
+                                if (pv && pc >= 0) {
+                                    const uint4 val = lds128(stg + (uint32_t)(r * 64 + ((q ^ ((r >> 1) & 3)) << 4)));
+                                    *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(y) + (int64_t)pc * d.y_cstride + d.y_coff + chb) = val;
+                                    if (y2)
+                                        *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(y2) + (int64_t)pc * d.y2_cstride + d.y2_coff + chb) = val;
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    if (tr) {
+                        const long long e3 = clock64();
+                        et[0] += e1 - e0;
+                        et[1] += e2 - e1;
+                        et[2] += e3 - e2;
+                    }
                 }
             }
             // all of this warp's tcgen05.ld have completed: hand the buffer back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(acc, j));
+            if (mul_staged && lane == 0) mbar_arrive(mul_empty(li & 1));   // (__syncwarp above: every lane has read its row)
         }
         if (tr) {
             p.dbg[7] = w_full;
@@ -984,7 +1038,19 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     // transpose path is opt-in: RGBD_TC_STAGE=1)
     static const bool env_stage = getenv("RGBD_TC_STAGE") != nullptr;
     p.stage_epi = (env_stage && d->ntaps * p.kblocks <= 8 && d->y_dtype == RGBD_DT_BF16) ? 1 : 0;
-    const int kBudget = kRingBudget - (p.stage_epi ? kStageBytes : 0);
+    // gate operand through TMA: only worth its shared memory when the layer is epilogue / memory bound
+    p.mul_blocks = 0;
+    p.mul_bytes = 0;
+    const bool mul_tma = d->epi == RGBD_EPI_GATE && d->mul != nullptr && d->o_step == 1 && d->y_dtype == RGBD_DT_BF16 &&
+                         ((d->mul_cstride | d->mul_coff) & 7) == 0 && ((uintptr_t)d->mul & 15) == 0 &&
+                         (d->Cout & 15) == 0 && d->ntaps * p.kblocks <= 8;
+    if (mul_tma) {
+        p.mul_blocks = (p.BN + 63) / 64;
+        p.mul_bytes = p.MT * 128 * 128;
+    }
+    // (these few small-K layers may use the whole SM: 220 KB in total, double-buffered gate tiles included)
+    const int kBudget = p.mul_blocks ? 220 * 1024 - 1024 - 2 * p.mul_blocks * p.mul_bytes
+                                     : kRingBudget - (p.stage_epi ? kStageBytes : 0);
     // Weight stages hold up to 3 consecutive taps (<= 36 KB): one barrier round trip + commit per stage
     // costs an issuing thread ~600 cycles, which 4 MMAs per accumulator do not cover.
     int max_group_taps = 1;
@@ -1019,7 +1085,8 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     RGBD_CHECK_ARG(total < 2147483647L, "too many tiles");
     p.total_tiles = (int)total;
     pl->smem = (size_t)p.nA * p.a_bytes + (size_t)p.nB * p.tps * p.b_bytes + 1024 /*align*/ +
-               8 * (2 * kMaxA + 2 * kMaxB + 8) + 16 + 128 + 4 * (size_t)d->cout_pad + 64 + (p.stage_epi ? kStageBytes : 0);
+               8 * (2 * kMaxA + 2 * kMaxB + 12) + 16 + 128 + 4 * (size_t)d->cout_pad + 64 + (p.stage_epi ? kStageBytes : 0) +
+               (p.mul_blocks ? 1024 + 2 * (size_t)p.mul_blocks * p.mul_bytes : 0);
     if (pl->smem < (size_t)kMinSmem) pl->smem = kMinSmem;
     static int num_sms = 0;
     if (num_sms == 0) {
@@ -1067,6 +1134,18 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     }
     p.rmap = p.amap[0];
     p.emap = p.bmap;
+    p.mmap = p.amap[0];
+    if (p.mul_blocks) {
+        cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->N};
+        cuuint64_t strides[3] = {(cuuint64_t)d->mul_cstride * 2, (cuuint64_t)d->Wo * d->mul_cstride * 2,
+                                 (cuuint64_t)d->Ho * d->Wo * d->mul_cstride * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)p.P, (cuuint32_t)p.R, 1};
+        rc = encode_map(&p.mmap, reinterpret_cast<const char *>(d->mul) + (int64_t)d->mul_coff * 2, 4, dims, strides, box);
+        if (rc) {
+            delete pl;
+            return rc;
+        }
+    }
     if (p.res_blocks) {
         cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->N};
         cuuint64_t strides[3] = {(cuuint64_t)d->res_cstride * 2, (cuuint64_t)d->Wo * d->res_cstride * 2,
@@ -1092,7 +1171,7 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     }
     static bool configured = false;
     if (!configured) {
-        const int cap = 200 * 1024;
+        const int cap = 227 * 1024;
         cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
