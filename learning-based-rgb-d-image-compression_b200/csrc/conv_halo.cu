@@ -123,6 +123,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Programmatic dependent launch: a conv kernel is launched while its predecessor in the stream is still in its
+// tail; everything up to griddep_wait() (TMEM allocation, barrier init, bias staging, descriptor fetch) overlaps
+// that tail, and nothing that reads or writes activation memory happens before it.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -393,6 +398,7 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
             int mli = 0;
             const bool tr = p.dbg != nullptr && blockIdx.x == 0;
             long long w_empty = 0;
+            griddep_wait();
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord tc = tile_coord(p, tile);
                 for (int g = 0; g < p.ngroups; ++g) {
@@ -425,6 +431,9 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                     ++mli;
                 }
             }
+            // this CTA has requested its last input: the next kernel of the stream may start its prologue on the
+            // SMs that drain first (it launches once every CTA of this grid got here or exited)
+            griddep_launch();
             if (tr) p.dbg[0] = w_empty;
         }
     } else if (warp == 1) {
@@ -433,6 +442,7 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
             RingPos rbp = {0, 0};
             const bool tr = p.dbg != nullptr && blockIdx.x == 0;
             long long w_empty = 0;
+            griddep_wait();   // per-image filters (rgbd_scale_weights) are produced by the previous kernel
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord tc = tile_coord(p, tile);
                 for (int g = 0; g < p.ngroups; ++g) {
@@ -594,6 +604,7 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                             (y2 == nullptr || y2_vec) && (d.Cout & 7) == 0;
         const uint32_t stg = stage_base + (uint32_t)(warp - kFirstEpiWarp) * 2048u;
         int li = 0;
+        griddep_wait();   // the epilogue reads (residual / gate / bilinear operands) and writes activation memory
         const bool tr = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == kFirstEpiWarp * 32;
         long long w_full = 0, et[3] = {0, 0, 0};
         const long long t_begin = tr ? clock64() : 0;
@@ -1047,6 +1058,8 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     if (mul_tma) {
         p.mul_blocks = (p.BN + 63) / 64;
         p.mul_bytes = p.MT * 128 * 128;
+        // needs room for two A and two weight stages beside the double-buffered tiles; else the epilogue loads it
+        if (220 * 1024 - 1024 - 2 * p.mul_blocks * p.mul_bytes < 2 * p.a_bytes + 2 * p.b_bytes) p.mul_blocks = p.mul_bytes = 0;
     }
     // (these few small-K layers may use the whole SM: 220 KB in total, double-buffered gate tiles included)
     const int kBudget = p.mul_blocks ? 220 * 1024 - 1024 - 2 * p.mul_blocks * p.mul_bytes
@@ -1191,7 +1204,18 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
 extern "C" int rgbd_conv_tc_run(const rgbd_conv_tc_plan *pl, void *stream) {
     RGBD_CHECK_ARG(pl != nullptr, "null plan");
     cudaStream_t st = (cudaStream_t)stream;
-#define RGBD_TC_LAUNCH(T, E) conv_halo_kernel<T, E><<<pl->grid, kThreads, pl->smem, st>>>(pl->p)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = pl->grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl->smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = getenv("RGBD_TC_NOPDL") == nullptr;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+#define RGBD_TC_LAUNCH(T, E) cudaLaunchKernelEx(&cfg, conv_halo_kernel<T, E>, pl->p)
     if (pl->out_f32) {
         if (pl->epi == RGBD_EPI_GATE) RGBD_TC_LAUNCH(float, 1);
         else if (pl->epi == RGBD_EPI_BILERP) RGBD_TC_LAUNCH(float, 2);
