@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int kWarpsPerBlock = 2;
+constexpr int kWarpsPerBlock = 4;   // fewer, fatter blocks: each holds a 57 KB table copy that can fence a conv CTA off its SM
 constexpr uint64_t kRansL = 1ull << 31;
 constexpr int kMaxTables = 256;
 constexpr uint32_t kFull = 0xffffffffu;
