@@ -286,7 +286,7 @@ def run_b200(args):
             "roofline": {"bound": "tensor", "achieved": roof["tflops"], "peak": tens_peak, "unit": "TFLOP/s",
                          "frac": roof["tflops"] / tens_peak, "traffic": None,
                          "kernel": roof["kernel"], "launches": roof["launches"], "peak_source": pk_src + " bf16 sustained",
-                         "share_of_step": S * roof["ms"] / (ms / K), "algorithmic_gflop_per_pair": GFLOP_PER_PAIR,
+                         "share_of_step": S * roof["ms"] / (ms / K), "algorithmic_gflop_per_pair": GFLOP_PER_PAIR, "by_class": roof["by_class"],
                          "whole_step_tflops": GFLOP_PER_PAIR * pairs_per_step * K / ms},
             "quality": stats,
         }
@@ -298,12 +298,17 @@ def run_b200(args):
 
 
 def conv_roofline(net, B, Hp, Wp, dev, dec_slot=0):
-    """Algorithmic conv flops / sum of conv launch durations for one encoder + decoder pass."""
+    """Algorithmic conv flops / sum of conv launch durations for one encoder + decoder pass, plus the same split
+    by which roof bounds each launch (arithmetic intensity above / below the ridge of the measured peaks)."""
     import ctypes as C
     import torch
+    pk, _ = peaks()
+    ridge = pk["bf16_tflops_sustained"] * 1e12 / (pk["hbm_gbs"] * 1e9)     # flop per byte
     total_ms, total_flops, n = 0.0, 0.0, 0
+    cls = {"tensor": [0.0, 0.0, 0.0, 0], "hbm": [0.0, 0.0, 0.0, 0]}       # ms, flops, bytes, launches
     with torch.cuda.device(dev):
-        for prog in (net._program("encoder", B, Hp, Wp), net._program("decoder", B, Hp // 64, Wp // 64, slot=dec_slot)):   # plans the timed run used: their buffers hold real streams
+        for prog in (net._program("encoder", B, Hp, Wp),
+                     net._program("decoder", B, Hp // 64, Wp // 64, slot=dec_slot)):   # plans the timed run used: their buffers hold real streams
             sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             evs = []
             for op in prog.ops:
@@ -312,15 +317,31 @@ def conv_roofline(net, B, Hp, Wp, dev, dec_slot=0):
                     a.record()
                     op(sp)
                     b.record()
-                    evs.append((a, b))
+                    evs.append((a, b, op))
                 else:
                     op(sp)
             torch.cuda.synchronize(dev)
-            total_ms += sum(a.elapsed_time(b) for a, b in evs)
+            for a, b, op in evs:
+                ms = a.elapsed_time(b)
+                total_ms += ms
+                c = cls["tensor" if op.flops / max(1, op.bytes) >= ridge else "hbm"]
+                c[0] += ms
+                c[1] += op.flops
+                c[2] += op.bytes
+                c[3] += 1
             total_flops += prog.flops
             n += len(evs)
-    return {"tflops": total_flops / (total_ms / 1e3) / 1e12, "ms": total_ms, "launches": n,
-            "kernel": "conv_simt_kernel" if net.precision == "fp32" else "conv_tc_kernel (tcgen05 implicit GEMM; + conv_simt for the fp32-input h_a layer)"}
+    by_class = {
+        "ridge_flop_per_byte": round(ridge, 1),
+        "tensor_bound_launches": {"launches": cls["tensor"][3], "ms": round(cls["tensor"][0], 3),
+                                  "tflops": round(cls["tensor"][1] / max(1e-9, cls["tensor"][0]) / 1e9, 1),
+                                  "frac_of_bf16_peak": round(cls["tensor"][1] / max(1e-9, cls["tensor"][0]) / 1e9 / pk["bf16_tflops_sustained"], 3)},
+        "hbm_bound_launches": {"launches": cls["hbm"][3], "ms": round(cls["hbm"][0], 3),
+                               "gbs": round(cls["hbm"][2] / max(1e-9, cls["hbm"][0]) / 1e6, 1),
+                               "frac_of_hbm_peak": round(cls["hbm"][2] / max(1e-9, cls["hbm"][0]) / 1e6 / pk["hbm_gbs"], 3)},
+    }
+    return {"tflops": total_flops / (total_ms / 1e3) / 1e12, "ms": total_ms, "launches": n, "by_class": by_class,
+            "kernel": "conv_simt_kernel" if net.precision == "fp32" else "conv_halo_kernel (tcgen05 implicit GEMM, halo-resident A tiles)"}
 
 
 if __name__ == "__main__":

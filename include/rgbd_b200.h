@@ -46,6 +46,9 @@ extern "C" {
 #define RGBD_EPI_LINEAR 0   /* y = act(v + res)                  res optional            */
 #define RGBD_EPI_GATE 1     /* y = res + mul * sigmoid(v)        res optional, mul required */
 #define RGBD_EPI_BILERP 2   /* y = act(v + bilinear_upsample(res)) res = small NHWC map     */
+#define RGBD_EPI_SHUFFLE2 3 /* tensor-core path only: the 16 accumulator columns are 4 output parities x 4 channels
+                               (column 4*(2*py+px)+c); site (sy, sx) stores act(v) at pixels (2*sy+py, 2*sx+px), c < Cout <= 4:
+                               a ConvTranspose2d(k5, s2, p2, op1) with few output channels as ONE 3x3 launch */
 
 #define RGBD_MAX_TAPS 25
 

@@ -383,7 +383,11 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
     }
     if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
     if (warp == 3) {
-        for (int i = lane; i < d.cout_pad; i += 32) bias_s[i] = (d.bias && i < d.Cout) ? d.bias[i] : 0.f;
+        if (d.epi == RGBD_EPI_SHUFFLE2) {   // columns are (parity, channel): every parity gets the channel's bias
+            if (lane < 16) bias_s[lane] = (d.bias && (lane & 3) < d.Cout) ? d.bias[lane & 3] : 0.f;
+        } else {
+            for (int i = lane; i < d.cout_pad; i += 32) bias_s[i] = (d.bias && i < d.Cout) ? d.bias[i] : 0.f;
+        }
         if (lane < RGBD_MAX_TAPS) shift_s[lane] = (uint32_t)((int)p.t_shift[lane] * 8);
     }
     tc_fence_before();
@@ -660,6 +664,20 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rv[i]);
+                if constexpr (kEpi == RGBD_EPI_SHUFFLE2) {
+                    // 16 columns = 4 output parities x 4 channels of a stride-2 transposed conv: pixel shuffle
+                    if (valid) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int64_t pix = ((int64_t)tc.n * d.Ho + 2 * sy + (q >> 1)) * d.Wo + 2 * sx + (q & 1);
+                            TOut *dst = y + pix * d.y_cstride + d.y_coff;
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch)
+                                if (ch < d.Cout) ElemIO<TOut>::st(dst + ch, act_fn(v[4 * q + ch] + bias_s[4 * q + ch], slope));
+                        }
+                    }
+                    return;
+                }
                 const int co = tc.co0 + c * 16;
                 const int nvalid = d.Cout - co;
                 uint4 cr[2] = {pr[0], pr[1]}, cm[2] = {pm[0], pm[1]};
@@ -750,7 +768,7 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                     }
                 }
             };
-            if constexpr (kGate || kEpi == RGBD_EPI_BILERP) {
+            if constexpr (kGate || kEpi == RGBD_EPI_BILERP || kEpi == RGBD_EPI_SHUFFLE2) {
                 // these epilogues keep their operands in registers too: one accumulator chunk in flight (no spills)
                 for (int c = 2 * cbfirst; c < nchunks; c = chunk_after(c)) {
                     tmem_ld16_issue(trow + (uint32_t)(c * 16), r0);
@@ -1191,6 +1209,8 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
         cudaFuncSetAttribute(conv_halo_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         cudaFuncSetAttribute(conv_halo_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         cudaFuncSetAttribute(conv_halo_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(conv_halo_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         configured = true;
     }
     if (getenv("RGBD_TC_VERBOSE"))
@@ -1219,10 +1239,12 @@ extern "C" int rgbd_conv_tc_run(const rgbd_conv_tc_plan *pl, void *stream) {
     if (pl->out_f32) {
         if (pl->epi == RGBD_EPI_GATE) RGBD_TC_LAUNCH(float, 1);
         else if (pl->epi == RGBD_EPI_BILERP) RGBD_TC_LAUNCH(float, 2);
+        else if (pl->epi == RGBD_EPI_SHUFFLE2) RGBD_TC_LAUNCH(float, 3);
         else RGBD_TC_LAUNCH(float, 0);
     } else {
         if (pl->epi == RGBD_EPI_GATE) RGBD_TC_LAUNCH(__nv_bfloat16, 1);
         else if (pl->epi == RGBD_EPI_BILERP) RGBD_TC_LAUNCH(__nv_bfloat16, 2);
+        else if (pl->epi == RGBD_EPI_SHUFFLE2) RGBD_TC_LAUNCH(__nv_bfloat16, 3);
         else RGBD_TC_LAUNCH(__nv_bfloat16, 0);
     }
 #undef RGBD_TC_LAUNCH

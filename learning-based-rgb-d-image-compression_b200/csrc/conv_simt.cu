@@ -281,7 +281,11 @@ extern "C" int rgbd_conv_validate(const rgbd_conv_desc *d) {
     RGBD_CHECK_ARG(d->ntaps > 0 && d->ntaps <= RGBD_MAX_TAPS, "ntaps");
     RGBD_CHECK_ARG(d->cout_pad >= d->Cout && (d->cout_pad & 15) == 0, "cout_pad must be a multiple of 16 >= Cout");
     RGBD_CHECK_ARG(d->x_coff + d->Cin <= d->x_cstride && d->y_coff + d->Cout <= d->y_cstride, "channel view");
-    RGBD_CHECK_ARG(d->epi >= 0 && d->epi <= 2, "epi");
+    RGBD_CHECK_ARG(d->epi >= 0 && d->epi <= 3, "epi");
+    RGBD_CHECK_ARG(d->epi != RGBD_EPI_SHUFFLE2 ||
+                       (d->o_step == 2 && d->o_off_y == 0 && d->o_off_x == 0 && d->cout_pad == 16 && d->Cout <= 4 &&
+                        (d->Hs - 1) * 2 + 1 < d->Ho && (d->Ws - 1) * 2 + 1 < d->Wo && !d->res && !d->mul && !d->y2),
+                   "SHUFFLE2 epilogue: o_step 2, no offsets, cout_pad 16, Cout <= 4, no res / mul / y2");
     RGBD_CHECK_ARG(d->epi != RGBD_EPI_GATE || d->mul, "GATE epilogue needs mul");
     RGBD_CHECK_ARG(d->epi != RGBD_EPI_BILERP || (d->res && d->res_H > 0 && d->res_W > 0), "BILERP needs res map");
     RGBD_CHECK_ARG((d->x_dtype | 1) == 1 && (d->y_dtype | 1) == 1, "dtype");
@@ -291,6 +295,7 @@ extern "C" int rgbd_conv_validate(const rgbd_conv_desc *d) {
 extern "C" int rgbd_conv_simt(const rgbd_conv_desc *d, void *stream) {
     int rc = rgbd_conv_validate(d);
     if (rc) return rc;
+    RGBD_CHECK_ARG(d->epi != RGBD_EPI_SHUFFLE2, "SHUFFLE2 epilogue exists on the tensor-core path only");
     cudaStream_t st = (cudaStream_t)stream;
     if (d->x_dtype == RGBD_DT_F32 && d->y_dtype == RGBD_DT_F32) launch_simt<float, float>(d, st);
     else if (d->x_dtype == RGBD_DT_BF16 && d->y_dtype == RGBD_DT_BF16) launch_simt<__nv_bfloat16, __nv_bfloat16>(d, st);

@@ -104,6 +104,27 @@ class PackedConv:
             self._wtc = w.contiguous()
         return self._wtc
 
+    @property
+    def wtc_shuffle(self):
+        """ConvTranspose2d(5, 2, 2, output_padding=1) with Cout <= 4 as ONE 3x3 conv over the input lattice whose 16
+        output columns are (output parity, channel): bf16 [9 union taps][16][cin_pad].  Union tap (dy, dx) in
+        {-1,0,1}^2 feeds parity (py, px) through filter tap (ky, kx) = (py + 2 - 2 dy, px + 2 - 2 dx) when that
+        lies inside the 5x5 filter (same arithmetic as launches(): dy = (py + p - ky) / 2)."""
+        if getattr(self, "_wtc_shuffle", None) is None:
+            assert self.transposed and self.k == 5 and self.stride == 2 and self.pad == 2 and self.Cout <= 4
+            T, cin, cp = self.w32.shape
+            self.cin_pad = (cin + 63) // 64 * 64
+            w = torch.zeros(9, 16, self.cin_pad, device=self.w32.device, dtype=torch.float32)
+            for u, (dy, dx) in enumerate((a, b) for a in (-1, 0, 1) for b in (-1, 0, 1)):
+                for py in range(2):
+                    for px in range(2):
+                        ky, kx = py + 2 - 2 * dy, px + 2 - 2 * dx
+                        if 0 <= ky < 5 and 0 <= kx < 5:
+                            q = 2 * py + px
+                            w[u, 4 * q:4 * q + self.Cout, :cin] = self.w32[ky * 5 + kx, :, :self.Cout].t()
+            self._wtc_shuffle = w.to(torch.bfloat16).contiguous()
+        return self._wtc_shuffle
+
     def launches(self, H, W):
         """-> (Ho, Wo, [dict(Hs, Ws, o_step, o_off_y, o_off_x, i_step, taps=[(dy, dx, wtap)])])"""
         k, s, p = self.k, self.stride, self.pad
@@ -265,6 +286,13 @@ class Builder:
             self.op("rgbd_scale_channels", x.ptr(), scaled.ptr(), _DT[x.dtype], in_scale.data_ptr(), x.N, x.H * x.W,
                     x.C, x.cstride, x.coff, scaled.cstride, scaled.coff)
             x, in_scale = scaled, None
+        shuffle = (use_tc and pc.transposed and pc.stride == 2 and pc.Cout <= 4 and res is None and mul is None
+                   and y2 is None and in_scale is None and epi == L.EPI_LINEAR)
+        if shuffle:
+            # the 4 output-parity launches of a transposed conv with <= 4 output channels fused into one 3x3 launch
+            # (N = 16 columns = parity x channel, pixel-shuffle epilogue): the input is read once instead of 4 times
+            launches = [dict(Hs=x.H, Ws=x.W, o_step=2, o_off_y=0, o_off_x=0, i_step=1, shuffle=True,
+                             taps=[(dy, dx, u) for u, (dy, dx) in enumerate((a, b_) for a in (-1, 0, 1) for b_ in (-1, 0, 1))])]
         for ln in launches:
             d = L.ConvDesc()
             d.x, d.y, d.w = x.ptr(), out.ptr(), pc.w32.data_ptr()
@@ -293,15 +321,17 @@ class Builder:
             if mul is not None:
                 assert mul.dtype == x.dtype and (mul.H, mul.W, mul.C) == (Ho, Wo, pc.Cout)
                 d.mul, d.mul_cstride, d.mul_coff = mul.ptr(), mul.cstride, mul.coff
-            d.act, d.epi = act, epi
+            d.act, d.epi = act, (L.EPI_SHUFFLE2 if ln.get("shuffle") else epi)
             d.x_dtype, d.y_dtype = _DT[x.dtype], _DT[out.dtype]
-            d.cout_pad = pc.cout_pad
+            d.cout_pad = 16 if ln.get("shuffle") else pc.cout_pad
             self.prog.keep.append(d)
             if use_tc:
                 d.w = pc.wtc.data_ptr()
                 if w_folded is not None:
                     d.w = w_folded.data_ptr()
                     d.w_image_stride = pc.w32.shape[0]
+                if ln.get("shuffle"):
+                    d.w = pc.wtc_shuffle.data_ptr()
                 handle = C.c_void_p()
                 L.check(L.load().rgbd_conv_tc_plan_create(C.byref(d), pc.cin_pad, C.byref(handle)),
                         "rgbd_conv_tc_plan_create")
@@ -316,8 +346,17 @@ class Builder:
             run.is_tc = use_tc
             kind = ("deconv" if pc.transposed else "conv") + f"{pc.k}x{pc.k}" + (f"s{pc.stride}" if pc.stride > 1 else "")
             run.label = f"{'tc' if use_tc else 'simt'} {kind} {pc.Cin}->{pc.Cout} @{ln['Hs']}x{ln['Ws']}"
-            run.flops = 2 * x.N * ln["Hs"] * ln["Ws"] * len(ln["taps"]) * pc.flop_cin * pc.Cout
+            # dense algorithmic count; the fused transposed conv still counts its 25 filter taps
+            run.flops = 2 * x.N * ln["Hs"] * ln["Ws"] * (25 if ln.get("shuffle") else len(ln["taps"])) * pc.flop_cin * pc.Cout
             self.prog.flops += run.flops
+            # algorithmic HBM bytes of this launch: the input once (shared by the parity launches of a transposed
+            # conv), the output lattice it writes (+ second copy), residual / gate operands, the weights
+            esz, osz = x.buf.element_size(), out.buf.element_size()
+            opix = x.N * ln["Hs"] * ln["Ws"] * (4 if ln.get("shuffle") else 1)
+            run.bytes = (x.N * x.H * x.W * x.C * esz // len(launches) + opix * pc.Cout * osz * (2 if y2 is not None else 1)
+                         + (opix * pc.Cout * esz if res is not None and epi != L.EPI_BILERP else 0)
+                         + (opix * pc.Cout * esz if mul is not None else 0)
+                         + len(ln["taps"]) * pc.Cin * pc.Cout * 2)
         self.prog.keep.extend([pc, x.buf, out.buf])
         if scaled is not None:
             self.release(scaled)

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "librgbd_b200.so")
 
 DT_F32, DT_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
-EPI_LINEAR, EPI_GATE, EPI_BILERP = 0, 1, 2
+EPI_LINEAR, EPI_GATE, EPI_BILERP, EPI_SHUFFLE2 = 0, 1, 2, 3
 MAX_TAPS = 25
 
 

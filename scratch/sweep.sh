@@ -1,11 +1,7 @@
 #!/bin/bash
-i=0
-while read -r cfg; do
-  i=$((i+1))
-  python bench.py --no-cpu-baseline $cfg > gpurun_out/sweep_$i.log 2>&1
-  echo "== $cfg (rc $?)"
-  tail -1 gpurun_out/sweep_$i.log | cut -c1-160
-done <<'CFGS'
---slots 8 --batch 16 --steps 4
---slots 6 --batch 16 --steps 4
-CFGS
+timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "conv_tc" 2>&1 | tail -1
+for v in 96 0; do
+  RGBD_TC_SMALLRING=$v python bench.py --no-cpu-baseline > gpurun_out/sweep_ring$v.log 2>&1
+  echo "== smallring $v (rc $?)"
+  tail -1 gpurun_out/sweep_ring$v.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['roofline']['frac'])"
+done

@@ -320,6 +320,7 @@ TC_CONVS = [
     ("5x5_512_384", lambda: nn.Conv2d(512, 384, 5, 1, 2), (1, 512, 8, 10)),
     ("deconv5s2_192", lambda: nn.ConvTranspose2d(192, 192, 5, 2, padding=2, output_padding=1), (1, 192, 9, 11)),
     ("deconv5s2_to3", lambda: nn.ConvTranspose2d(192, 3, 5, 2, padding=2, output_padding=1), (2, 192, 16, 16)),
+    ("deconv5s2_to1_ragged", lambda: nn.ConvTranspose2d(192, 1, 5, 2, padding=2, output_padding=1), (2, 192, 19, 45)),
     ("deconv3s1_960_640", lambda: nn.ConvTranspose2d(960, 640, 3, 1, padding=1), (1, 960, 8, 10)),
     # two-accumulator super-tiles, several tiles per row, halo rows shared between the M tiles
     ("3x3_96_96_wide", lambda: nn.Conv2d(96, 96, 3, 1, 1), (2, 96, 64, 80)),
