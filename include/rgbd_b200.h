@@ -144,7 +144,10 @@ int rgbd_maxpool7s3(const void *x, void *y, int32_t dtype, int32_t N, int32_t H,
                     int32_t C, void *stream);
 /* NCHW fp32 image -> NHWC (dtype), and back with optional clamp to [0,1] (elic_united.py:452).
  * split3 != 0 writes 3*C channels [hi | lo | hi] (hi = dtype(x), lo = dtype(x - hi)): the two-term
- * bf16 expansion the tensor-core first layer consumes against weights packed [w_hi | w_hi | w_lo]. */
+ * bf16 expansion the tensor-core first layer consumes against weights packed [w_hi | w_hi | w_lo].
+ * split3 == 2 additionally folds 2x2 pixel blocks into channels (space-to-depth: y is [N, H/2, W/2, 4*3*C], channel
+ * block 2*ry+rx = input pixel (2Y+ry, 2X+rx)), which turns the 5x5 stride-2 first conv into a 3x3 stride-1 conv with one
+ * tap group (H, W even). */
 int rgbd_nchw_to_nhwc(const float *x, void *y, int32_t dtype, int32_t N, int32_t C, int32_t H,
                       int32_t W, int32_t y_cstride, int32_t y_coff, int32_t split3, void *stream);
 int rgbd_nhwc_to_nchw(const void *x, int32_t dtype, float *y, int32_t N, int32_t C, int32_t H,

@@ -101,8 +101,20 @@ __global__ void nchw_to_nhwc_kernel(const float *__restrict__ x, T *__restrict__
         const int64_t hw = e % ((int64_t)H * W);
         const int c = (int)((e / ((int64_t)H * W)) % C);
         const int n = (int)(e / ((int64_t)H * W * C));
-        T *dst = y + ((int64_t)n * H * W + hw) * cstride + coff + c;
         const float v = x[e];
+        if (split3 == 2) {
+            // split + space-to-depth: pixel (2Y + ry, 2X + rx) -> pixel (Y, X) of an H/2 x W/2 map, channel block
+            // (2 ry + rx) of 3C channels [hi | lo | hi]
+            const int yy = (int)(hw / W), xx = (int)(hw % W);
+            T *dst = y + (((int64_t)n * (H / 2) + (yy >> 1)) * (W / 2) + (xx >> 1)) * cstride + coff +
+                     (2 * (yy & 1) + (xx & 1)) * 3 * C + c;
+            const float hi = round_to<T>(v);
+            ElemIO<T>::st(dst, v);
+            ElemIO<T>::st(dst + C, v - hi);
+            ElemIO<T>::st(dst + 2 * C, v);
+            continue;
+        }
+        T *dst = y + ((int64_t)n * H * W + hw) * cstride + coff + c;
         ElemIO<T>::st(dst, v);
         if (split3) {
             const float hi = round_to<T>(v);

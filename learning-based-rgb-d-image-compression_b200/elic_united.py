@@ -160,12 +160,12 @@ class ELIC_united(nn.Module):
     def act_dtype(self):
         return torch.float32 if self.precision == "fp32" else torch.bfloat16
 
-    def _pc(self, mod, in_perm=None, split3=False):
+    def _pc(self, mod, in_perm=None, split3=False, s2d=False):
         if self._packed is None:
             self._packed = {}
-        key = (id(mod), split3)
+        key = (id(mod), split3, s2d)
         if key not in self._packed:
-            self._packed[key] = PackedConv(mod, self.device, in_perm, split3)
+            self._packed[key] = PackedConv(mod, self.device, in_perm, split3, s2d)
         return self._packed[key]
 
     def _dev32(self, key, make):
@@ -272,7 +272,8 @@ class ELIC_united(nn.Module):
 
             def step(mod, x, is_rgb):
                 if isinstance(mod, (nn.Conv2d, nn.ConvTranspose2d)):
-                    pc = self._pc(mod, split3=(x.C == 3 * mod.in_channels))
+                    s2d = x.C == 12 * mod.in_channels          # image layer on the space-to-depth map
+                    pc = self._pc(mod, split3=s2d or x.C == 3 * mod.in_channels, s2d=s2d)
                     Ho, Wo, _ = pc.launches(x.H, x.W)
                     return b.conv(pc, x, out=out_for(is_rgb, Ho, Wo, pc.Cout),
                                   out_dtype=final_dtype if last else None)
@@ -485,9 +486,11 @@ class ELIC_united(nn.Module):
         p = b.prog
         # bf16 tensor-core mode: the images enter as a two-term bf16 expansion [hi | lo | hi] so the first
         # layer keeps fp32-like accuracy (16-bit depth is represented exactly) at no extra MMA cost
-        split = 1 if b.tensor_cores else 0
-        x_r = b.alloc(B, H, W, 9 if split else 3)
-        x_d = b.alloc(B, H, W, 3 if split else 1)
+        # ... and as a space-to-depth map (2x2 pixel blocks -> channels), which turns the 5x5 stride-2 first conv
+        # into a 3x3 stride-1 conv with a single tap group (one halo load per tile instead of four parity loads)
+        split = 2 if b.tensor_cores else 0
+        x_r = b.alloc(B, H // 2, W // 2, 36) if split else b.alloc(B, H, W, 3)
+        x_d = b.alloc(B, H // 2, W // 2, 12) if split else b.alloc(B, H, W, 1)
         in_r = b.raw((B, 3, H, W), torch.float32)
         in_d = b.raw((B, 1, H, W), torch.float32)
         p.io["rgb"], p.io["depth"] = in_r, in_d

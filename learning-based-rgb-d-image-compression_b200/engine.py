@@ -49,7 +49,7 @@ class PackedConv:
     reference's torch.cat order).
     """
 
-    def __init__(self, mod, device, in_perm=None, split3=False):
+    def __init__(self, mod, device, in_perm=None, split3=False, s2d=False):
         w = mod.weight.detach().to(device=device, dtype=torch.float32)
         self.transposed = isinstance(mod, torch.nn.ConvTranspose2d)
         if self.transposed:
@@ -73,6 +73,25 @@ class PackedConv:
             hi = taps.to(torch.bfloat16).to(torch.float32)
             taps = torch.cat([hi, hi, taps - hi], dim=1)
             cin = self.Cin = 3 * cin
+        self.flop_taps = None
+        if s2d:
+            # Conv2d(k5, s2, p2) over an image == Conv2d(k3, s1, p1) over its space-to-depth map (rgbd_nchw_to_nhwc
+            # split3 = 2): tap (qy, qx) of parity block (ry, rx) is filter tap (dy, dx) = (2 qy + ry, 2 qx + rx)
+            assert not self.transposed and kh == 5 and self.stride == 2 and self.pad == 2
+            t3 = torch.zeros(9, 4 * cin, cout, device=device, dtype=torch.float32)
+            for qy in (-1, 0, 1):
+                for qx in (-1, 0, 1):
+                    for ry in range(2):
+                        for rx in range(2):
+                            dy, dx = 2 * qy + ry, 2 * qx + rx
+                            if -2 <= dy <= 2 and -2 <= dx <= 2:
+                                blk = 2 * ry + rx
+                                t3[(qy + 1) * 3 + qx + 1, blk * cin:(blk + 1) * cin] = taps[(dy + 2) * 5 + dx + 2]
+            taps = t3
+            self.flop_taps = 25          # algorithmic count stays the dense 5x5
+            self.k, self.stride, self.pad = 3, 1, 1
+            kh = kw = 3
+            cin = self.Cin = 4 * cin
         self.cout_pad = (cout + 15) // 16 * 16
         packed = torch.zeros(kh * kw, cin, self.cout_pad, device=device, dtype=torch.float32)
         packed[:, :, :cout] = taps
@@ -347,7 +366,8 @@ class Builder:
             kind = ("deconv" if pc.transposed else "conv") + f"{pc.k}x{pc.k}" + (f"s{pc.stride}" if pc.stride > 1 else "")
             run.label = f"{'tc' if use_tc else 'simt'} {kind} {pc.Cin}->{pc.Cout} @{ln['Hs']}x{ln['Ws']}"
             # dense algorithmic count; the fused transposed conv still counts its 25 filter taps
-            run.flops = 2 * x.N * ln["Hs"] * ln["Ws"] * (25 if ln.get("shuffle") else len(ln["taps"])) * pc.flop_cin * pc.Cout
+            ntap_alg = 25 if ln.get("shuffle") else (pc.flop_taps or len(ln["taps"]))
+            run.flops = 2 * x.N * ln["Hs"] * ln["Ws"] * ntap_alg * pc.flop_cin * pc.Cout
             self.prog.flops += run.flops
             # algorithmic HBM bytes of this launch: the input once (shared by the parity launches of a transposed
             # conv), the output lattice it writes (+ second copy), residual / gate operands, the weights

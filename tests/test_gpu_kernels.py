@@ -427,3 +427,14 @@ def test_split_bf16_first_layer_is_fp32_accurate():
             want = mod(img)
         got = out.torch().float().cpu().permute(0, 3, 1, 2)
         assert rel_err(got, want) < 5e-5, (cin, rel_err(got, want))
+        # the same layer on the space-to-depth map (what the codec uses): 3x3 stride 1, one tap group
+        b2 = Builder(torch.device(DEV), torch.bfloat16, tensor_cores=True)
+        x2 = b2.alloc(2, 32, 48, 12 * cin)
+        b2.op("rgbd_nchw_to_nhwc", src.data_ptr(), x2.ptr(), L.DT_BF16, 2, cin, 64, 96, x2.cstride, x2.coff, 2)
+        out2 = b2.conv(PackedConv(mod, torch.device(DEV), split3=True, s2d=True), x2, out_dtype=torch.float32)
+        assert b2.prog.n_tc == 1 and (out2.H, out2.W) == (32, 48)
+        b2.prog.run()
+        torch.cuda.synchronize()
+        got2 = out2.torch().float().cpu().permute(0, 3, 1, 2)
+        assert rel_err(got2, want) < 5e-5, (cin, rel_err(got2, want))
+        assert abs(b2.prog.flops - b.prog.flops) < 1
