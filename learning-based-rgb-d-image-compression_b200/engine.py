@@ -232,21 +232,61 @@ class Builder:
 
     # ---- memory ----
     def alloc(self, N, H, W, Cc, dtype=None, zero=False):
+        """NHWC buffer carved from the plan's byte arena (a small heap allocator: best-fit free ranges, split on
+        allocation, neighbours coalesced on release).  The launch list is serial on one stream, so storage
+        released at build time is dead by the time a later op runs; the high-resolution buffers of g_a / g_s
+        thereby back the context-model and low-resolution tensors as well."""
         dtype = dtype or self.act_dtype
         # 16-byte aligned pixel rows (TMA global strides, vector epilogue stores)
         Cp = (Cc + 7) // 8 * 8 if dtype == torch.bfloat16 else Cc
-        key = ((N, H, W, Cp), dtype)
-        free = self.prog.pool.setdefault(key, [])
-        if free and not zero:
-            t = free.pop()
+        shape = (N, H, W, Cp)
+        esz = torch.empty((), dtype=dtype).element_size()
+        nbytes = N * H * W * Cp * esz
+        need = (nbytes + 1023) // 1024 * 1024          # 1 KB granules keep every carve aligned
+        chunks = self.prog.pool.setdefault("chunks", [])   # [tensor, free ranges [(off, size)] sorted by off]
+        pick = None
+        if not zero:
+            for ci, (_, free) in enumerate(chunks):
+                for ri, (off, size) in enumerate(free):
+                    if size >= need and (pick is None or size < pick[2]):
+                        pick = (ci, ri, size)
+        if pick is None:
+            # new chunk: at least 64 MB per image, so that later tensors pack into its tail instead of each
+            # opening a chunk of their own (zero-initialised buffers get an exact, private chunk)
+            size = need if zero else max(need, (64 << 20) * N)
+            store = (torch.zeros if zero else torch.empty)((size,), device=self.device, dtype=torch.uint8)
+            self.prog.bytes += size
+            chunks.append([store, [(need, size - need)] if size > need else []])
+            ci, off = len(chunks) - 1, 0
         else:
-            t = (torch.zeros if zero else torch.empty)((N, H, W, Cp), device=self.device, dtype=dtype)
-            self.prog.bytes += t.numel() * t.element_size()
+            ci, ri, size = pick
+            off = chunks[ci][1][ri][0]
+            if size > need:
+                chunks[ci][1][ri] = (off + need, size - need)
+            else:
+                del chunks[ci][1][ri]
+        t = chunks[ci][0][off:off + nbytes].view(dtype).view(shape)
+        t._rgbd_range = [ci, off, need]      # emptied on release (two views of one buffer release it once)
         return View(t, 0, Cc)
 
     def release(self, *views):
+        chunks = self.prog.pool.get("chunks", [])
         for v in views:
-            self.prog.pool.setdefault((tuple(v.buf.shape), v.buf.dtype), []).append(v.buf)
+            rng = getattr(v.buf, "_rgbd_range", None)
+            if not rng:
+                continue
+            ci, off, size = rng
+            del rng[:]
+            free = chunks[ci][1]
+            free.append((off, size))
+            free.sort()
+            merged = []
+            for o, sz in free:
+                if merged and merged[-1][0] + merged[-1][1] == o:
+                    merged[-1] = (merged[-1][0], merged[-1][1] + sz)
+                else:
+                    merged.append((o, sz))
+            chunks[ci][1] = merged
 
     def raw(self, shape, dtype, zero=False):
         t = (torch.zeros if zero else torch.empty)(shape, device=self.device, dtype=dtype)

@@ -1,7 +1,13 @@
 #!/bin/bash
-timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "conv_tc" 2>&1 | tail -1
-for v in 96 0; do
-  RGBD_TC_SMALLRING=$v python bench.py --no-cpu-baseline > gpurun_out/sweep_ring$v.log 2>&1
-  echo "== smallring $v (rc $?)"
-  tail -1 gpurun_out/sweep_ring$v.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['roofline']['frac'])"
-done
+i=0
+while read -r cfg; do
+  i=$((i+1))
+  python bench.py --no-cpu-baseline $cfg > gpurun_out/sweep_$i.log 2>&1
+  echo "== $cfg (rc $?)"
+  tail -1 gpurun_out/sweep_$i.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['config']['hbm_peak_gb'])" 2>/dev/null || tail -2 gpurun_out/sweep_$i.log | cut -c1-200
+done <<'CFGS'
+--slots 8 --batch 16
+--slots 8 --batch 20
+--slots 8 --batch 24
+--slots 6 --batch 24
+CFGS
