@@ -173,7 +173,7 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch or (2 if args.precision == "fp32" else 16)
+    B = args.batch or (2 if args.precision == "fp32" else 24)
 
     net = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4, precision=args.precision).eval()
     net.load_state_dict(rgbd_b200.synthetic.synthetic_state_dict(net, 0, args.preset))

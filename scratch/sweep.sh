@@ -6,8 +6,8 @@ while read -r cfg; do
   echo "== $cfg (rc $?)"
   tail -1 gpurun_out/sweep_$i.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['config']['hbm_peak_gb'])" 2>/dev/null || tail -2 gpurun_out/sweep_$i.log | cut -c1-200
 done <<'CFGS'
---slots 8 --batch 16
---slots 8 --batch 20
 --slots 8 --batch 24
---slots 6 --batch 24
+--slots 8 --batch 32
+--slots 10 --batch 24
+--slots 12 --batch 20
 CFGS
