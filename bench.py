@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("RGBD_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--slots", type=int, default=8, help="batches in flight per GPU (own program + CUDA stream each)")
     ap.add_argument("--graphs", type=int, default=1, help="replay each slot's launch list as a CUDA graph")
+    ap.add_argument("--threads", type=int, default=0, help="drive every pipeline slot from its own host thread")
     ap.add_argument("--preset", default="realistic")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
@@ -196,7 +197,7 @@ def run_b200(args):
     # convolutions of batches k+1..; one step = S batches of B pairs, every pair compressed AND
     # decompressed inside the timed region.
     from rgbd_b200.pipeline import RoundTripPipeline
-    pipe = RoundTripPipeline(net, S)
+    pipe = RoundTripPipeline(net, S, threads=bool(args.threads))
 
     def steps_device(k):
         jobs = [(rgb_d[sl[i % S]], depth_d[sl[i % S]]) for i in range(k * S)]
@@ -275,7 +276,7 @@ def run_b200(args):
             "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": f"ELIC_united compress+decompress, {world}x{S}x{B} pairs/step of "
                                    f"{args.height}x{args.width} (padded {Hp}x{Wp}), preset {args.preset}, "
-                                   f"weights calibrated random-init", "pairs_per_gpu": S * B, "batch": B, "slots_in_flight": S, "schedule": "pipelined: S compress + S decompress jobs in flight (rgbd_b200.pipeline)", "precision": args.precision, "cuda_graphs": bool(args.graphs),
+                                   f"weights calibrated random-init", "pairs_per_gpu": S * B, "batch": B, "slots_in_flight": S, "schedule": "pipelined: S compress + S decompress jobs in flight (rgbd_b200.pipeline)", "host_threads": bool(args.threads), "precision": args.precision, "cuda_graphs": bool(args.graphs),
                        "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
                        "hbm_peak_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
                        "parallelism": f"dp{world} (images sharded, no data-path collective)"},

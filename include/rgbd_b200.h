@@ -83,6 +83,8 @@ typedef struct rgbd_conv_desc {
     const void *res;        /* optional, dtype = x_dtype */
     const void *mul;        /* optional, dtype = x_dtype */
     const float *in_scale;  /* optional [N][Cin] per-image input-channel scale (SE folding) */
+    void *sched_ws;         /* tensor-core path: one zero-initialised int32 in device memory per plan, owned by the
+                               caller (the persistent kernel's tile counter; the kernel leaves it at zero) */
     int32_t N, H, W;        /* input dims */
     int32_t Cin, x_cstride, x_coff;
     int32_t Ho, Wo;         /* full output dims */

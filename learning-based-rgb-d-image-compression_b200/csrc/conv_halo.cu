@@ -48,6 +48,7 @@ constexpr int kMaxAStage = 52 * 1024;              // halo tile (one channel blo
 constexpr int kMinSmem = 120 * 1024;               // > half an SM: never two of these CTAs on one SM (512 TMEM columns each)
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMaxGroups = 4;
+constexpr int kTileQ = 4;                          // depth of the CTA's tile queue (dynamic scheduler)
 constexpr int kMaxBias = 1024;
 
 struct HParams {
@@ -350,10 +351,13 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
     auto tmem_empty_bar = [&](int a, int j) { return bar_base + 8u * (uint32_t)(2 * kMaxA + 2 * kMaxB + 4 + 2 * a + j); };
     auto mul_full = [&](int b) { return bar_base + 8u * (uint32_t)(2 * kMaxA + 2 * kMaxB + 8 + b); };
     auto mul_empty = [&](int b) { return bar_base + 8u * (uint32_t)(2 * kMaxA + 2 * kMaxB + 10 + b); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxA + 2 * kMaxB + 12);
+    auto tq_full = [&](int q) { return bar_base + 8u * (uint32_t)(2 * kMaxA + 2 * kMaxB + 12 + q); };
+    auto tq_empty = [&](int q) { return bar_base + 8u * (uint32_t)(2 * kMaxA + 2 * kMaxB + 12 + kTileQ + q); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxA + 2 * kMaxB + 12 + 2 * kTileQ);
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
     // per-tap A descriptor offsets (row shift * 128 B >> 4), then the bias
     uint32_t *shift_s = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot + 16u - raw));
+    volatile int *tq_s = reinterpret_cast<volatile int *>(smem_raw + (tmem_slot + 16u + 104u - raw));   // kTileQ tile indices
     float *bias_s = reinterpret_cast<float *>(smem_raw + (tmem_slot + 16u + 128u - raw));
     const uint32_t stage_base = tmem_slot + 16u + 128u + 4u * (uint32_t)d.cout_pad;   // 16-byte aligned (cout_pad % 16 == 0)
     // gate operand tiles (1024-byte aligned: the TMA 128-byte swizzle is a function of the address)
@@ -379,6 +383,11 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
             mbar_init(mul_full(b), 1);
             mbar_init(mul_empty(b), kEpiWarps);
         }
+        // tile queue: filled by the A producer, read by the B producer, the MMA issuer warps and the epilogue warps
+        for (int q = 0; q < kTileQ; ++q) {
+            mbar_init(tq_full(q), 1);
+            mbar_init(tq_empty(q), (uint32_t)(1 + p.MT + kEpiWarps));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -394,6 +403,18 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // Dynamic tile scheduler: tiles are handed out in index order from a global counter (p.d.sched_ws), so a CTA that
+    // starts late — its SM was busy with rANS coder blocks of another pipeline slot — does not hold the grid back: the
+    // other CTAs take its share.  The A producer thread draws the tile and publishes it through a small queue; every
+    // other role reads the k-th entry.  Which CTA computes a tile has no effect on the result.
+    auto next_tile = [&](int k) -> int {      // consumers: all lanes of the calling warp
+        const int q = k % kTileQ;
+        mbar_wait(tq_full(q), (uint32_t)((k / kTileQ) & 1));
+        const int t = tq_s[q];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tq_empty(q));
+        return t;
+    };
 
     if (warp == 0) {
         // =========================== A producer (halo tiles, residual tiles) ===========================
@@ -403,7 +424,21 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
             const bool tr = p.dbg != nullptr && blockIdx.x == 0;
             long long w_empty = 0;
             griddep_wait();
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int *counter = reinterpret_cast<int *>(d.sched_ws);
+            for (int k = 0;; ++k) {
+                // draw the next tile and publish it to the other roles
+                const int q = k % kTileQ;
+                mbar_wait(tq_empty(q), (uint32_t)((k / kTileQ) & 1) ^ 1u);
+                int tile = atomicAdd(counter, 1);
+                if (tile >= p.total_tiles) {
+                    // every CTA draws exactly one value past the end; the last of them re-arms the counter for the
+                    // next launch of this plan (stream order keeps that launch behind this one)
+                    if (tile == p.total_tiles + (int)gridDim.x - 1) atomicExch(counter, 0);
+                    tile = p.total_tiles;
+                }
+                tq_s[q] = tile;
+                mbar_arrive(tq_full(q));
+                if (tile >= p.total_tiles) break;
                 const TileCoord tc = tile_coord(p, tile);
                 for (int g = 0; g < p.ngroups; ++g) {
                     for (int kb = 0; kb < p.kblocks; ++kb, ra.next(p.nA)) {
@@ -442,12 +477,15 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
         }
     } else if (warp == 1) {
         // =========================== B producer (weights, identity tiles) ===========================
-        if (lane == 0) {
+        {
             RingPos rbp = {0, 0};
-            const bool tr = p.dbg != nullptr && blockIdx.x == 0;
+            const bool tr = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
             long long w_empty = 0;
             griddep_wait();   // per-image filters (rgbd_scale_weights) are produced by the previous kernel
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int k = 0;; ++k) {
+                const int tile = next_tile(k);      // whole warp; lane 0 issues the loads
+                if (tile >= p.total_tiles) break;
+                if (lane != 0) continue;
                 const TileCoord tc = tile_coord(p, tile);
                 for (int g = 0; g < p.ngroups; ++g) {
                     const int t0 = p.g_first[g], t1 = p.g_first[g + 1];
@@ -494,7 +532,9 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
             const uint32_t a_lo0 = (a_base >> 4) + (uint32_t)(j * 1024), b_lo0 = b_base >> 4;
             uint32_t a_lo = a_lo0, b_lo = b_lo0;     // descriptor start-address fields of the current ring stages
             const int kblocks = p.kblocks, ngroups = p.ngroups;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+            for (;; ++li) {
+                const int tile = next_tile(li);
+                if (tile >= p.total_tiles) break;
                 const TileCoord tc = tile_coord(p, tile);
                 const int acc = li & 1;
                 const uint32_t use = (uint32_t)(li >> 1);
@@ -612,7 +652,9 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
         const bool tr = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == kFirstEpiWarp * 32;
         long long w_full = 0, et[3] = {0, 0, 0};
         const long long t_begin = tr ? clock64() : 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+        for (;; ++li) {
+            const int tile = next_tile(li);
+            if (tile >= p.total_tiles) break;
             const TileCoord tc = tile_coord(p, tile);
             const int acc = li & 1;
             const uint32_t use = (uint32_t)(li >> 1);
@@ -932,6 +974,8 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     RGBD_CHECK_ARG(cin_pad >= d->Cin && (cin_pad % kBlockK) == 0, "cin_pad must be a multiple of 64 >= Cin");
     RGBD_CHECK_ARG(d->i_step == 1 || d->i_step == 2, "i_step must be 1 or 2");
     RGBD_CHECK_ARG(d->cout_pad <= kMaxBias, "cout_pad too large");
+    RGBD_CHECK_ARG(d->sched_ws != nullptr && ((uintptr_t)d->sched_ws & 3) == 0,
+                   "sched_ws: the caller provides a zero-initialised int32 in device memory per plan (tile counter)");
     for (int t = 0; t < d->ntaps; ++t)
         RGBD_CHECK_ARG(d->w_image_stride == 0 || d->w_image_stride > d->wtap[t], "w_image_stride must cover every tap");
     RGBD_CHECK_ARG((int64_t)d->N * d->Ho * d->Wo < 2147483647LL, "too many output pixels");
@@ -1116,7 +1160,7 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     RGBD_CHECK_ARG(total < 2147483647L, "too many tiles");
     p.total_tiles = (int)total;
     pl->smem = (size_t)p.nA * p.a_bytes + (size_t)p.nB * p.tps * p.b_bytes + 1024 /*align*/ +
-               8 * (2 * kMaxA + 2 * kMaxB + 12) + 16 + 128 + 4 * (size_t)d->cout_pad + 64 + (p.stage_epi ? kStageBytes : 0) +
+               8 * (2 * kMaxA + 2 * kMaxB + 12 + 2 * kTileQ) + 16 + 128 + 4 * (size_t)d->cout_pad + 64 + (p.stage_epi ? kStageBytes : 0) +
                (p.mul_blocks ? 1024 + 2 * (size_t)p.mul_blocks * p.mul_bytes : 0);
     if (pl->smem < (size_t)kMinSmem) pl->smem = kMinSmem;
     static int num_sms = 0;

@@ -227,6 +227,8 @@ class Builder:
         self.act_dtype = act_dtype
         self.prog = Program(device)
         self._wscratch = None   # per-image SE-folded filters of the layer being run (shared by all layers)
+        self._sched = None      # tile counters of the persistent conv kernels (one int32 per plan, zero between launches)
+        self._sched_used = 0
         # tcgen05 path: bf16 activations only
         self.tensor_cores = (act_dtype == torch.bfloat16) if tensor_cores is None else tensor_cores
 
@@ -385,6 +387,11 @@ class Builder:
             d.cout_pad = 16 if ln.get("shuffle") else pc.cout_pad
             self.prog.keep.append(d)
             if use_tc:
+                if self._sched is None or self._sched_used == self._sched.numel():
+                    self._sched = self.raw((4096,), torch.int32, zero=True)
+                    self._sched_used = 0
+                d.sched_ws = self._sched.data_ptr() + 4 * self._sched_used
+                self._sched_used += 1
                 d.w = pc.wtc.data_ptr()
                 if w_folded is not None:
                     d.w = w_folded.data_ptr()

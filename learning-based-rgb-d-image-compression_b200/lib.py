@@ -23,6 +23,7 @@ class ConvDesc(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("y", C.c_void_p), ("y2", C.c_void_p), ("w", C.c_void_p),
         ("bias", C.c_void_p), ("res", C.c_void_p), ("mul", C.c_void_p), ("in_scale", C.c_void_p),
+        ("sched_ws", C.c_void_p),
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("Cin", C.c_int32), ("x_cstride", C.c_int32), ("x_coff", C.c_int32),
         ("Ho", C.c_int32), ("Wo", C.c_int32),
