@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--slots", type=int, default=8, help="batches in flight per GPU (own program + CUDA stream each)")
     ap.add_argument("--graphs", type=int, default=1, help="replay each slot's launch list as a CUDA graph")
     ap.add_argument("--threads", type=int, default=0, help="drive every pipeline slot from its own host thread")
+    ap.add_argument("--dec-slots", type=int, default=0, help="decompress jobs in flight (default: = --slots)")
+    ap.add_argument("--hiprio", type=int, default=1, help="decoder slots on high-priority CUDA streams")
     ap.add_argument("--preset", default="realistic")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
@@ -190,14 +192,14 @@ def run_b200(args):
     rgb_d, depth_d = rgb_h.to(dev), depth_h.to(dev)
     Hp, Wp = rgb_h.shape[-2:]
     sl = [slice(i * B, (i + 1) * B) for i in range(S)]
-    host_out = [(torch.empty((B, 3, Hp, Wp)).pin_memory(), torch.empty((B, 1, Hp, Wp)).pin_memory()) for _ in range(S)]
+    host_out = [(torch.empty((B, 3, Hp, Wp)).pin_memory(), torch.empty((B, 1, Hp, Wp)).pin_memory()) for _ in range(max(S, args.dec_slots or S))]
 
     # Round-trip pipeline (rgbd_b200.pipeline): S compress jobs and S decompress jobs in flight, each on
     # its own stream + launch plan, so the decoder's serial rANS chain of batch k hides behind the
     # convolutions of batches k+1..; one step = S batches of B pairs, every pair compressed AND
     # decompressed inside the timed region.
     from rgbd_b200.pipeline import RoundTripPipeline
-    pipe = RoundTripPipeline(net, S, threads=bool(args.threads))
+    pipe = RoundTripPipeline(net, S, threads=bool(args.threads), high_priority_decode=bool(args.hiprio), dec_slots=args.dec_slots or None)
 
     def steps_device(k):
         jobs = [(rgb_d[sl[i % S]], depth_d[sl[i % S]]) for i in range(k * S)]

@@ -7,7 +7,7 @@ decompress jobs concurrently, each on its own CUDA stream and launch-plan instan
 (`compress_async` / `decompress_async` slots 0..S-1 and S..2S-1): while batch k is being decoded,
 batches k+1.. are already being analysed, so the serial chains hide behind the tensor-core work.
 
-With `threads=True` (default) every slot is driven by its own host thread (compress -> collect the
+With `threads=True` every slot is driven by its own host thread (compress -> collect the
 strings -> decompress, job after job): a slot that is waiting for its coder kernels or copying its
 bitstreams to the host does not hold back the submission of the other slots' work.  The CUDA calls
 and the ctypes launches release the GIL.
@@ -22,11 +22,23 @@ import torch
 
 
 class RoundTripPipeline:
-    def __init__(self, net, slots, threads=True):
+    def __init__(self, net, slots, threads=False, high_priority_decode=True, dec_slots=None):
         self.net = net
         self.S = max(1, int(slots))
+        # a decompress job lives ~2.5x longer than a compress job (its serial rANS chain): with the same number of
+        # launch plans, fewer compress slots and more decompress slots keep more of the chains in flight
+        self.D = self.S if dec_slots is None else max(1, int(dec_slots))
         self.threads = bool(threads)
         self._ready = set()     # (B, H, W) whose 2S launch plans (and CUDA graphs) exist
+        # The decoder's chain is ~260 small dependent kernels between its rANS chunks: on high-priority streams they
+        # are scheduled ahead of the other slots' pending big convolutions as soon as SMs drain, which keeps the
+        # chain's latency (and with it the number of slots needed to hide it) down.
+        if high_priority_decode:
+            device = next(net.parameters()).device
+            streams = net.__dict__.setdefault("_slot_streams", {})
+            for slot in range(self.S, self.S + self.D):
+                if slot not in streams:
+                    streams[slot] = torch.cuda.Stream(device, priority=-1)
 
     # ------------------------------------------------------------------ helpers
     def _input(self, n, slot, job, stage_input):
@@ -51,8 +63,10 @@ class RoundTripPipeline:
         if key in self._ready:
             return
         net, S = self.net, self.S
+        c = None
         for slot in range(S):
             c = net.compress_async(rgb, depth, slot=slot).result()
+        for slot in range(self.D):
             net.decompress_async(c["r_strings"], c["d_strings"], c["shape"], slot=S + slot).result(clone=False)
         torch.cuda.synchronize(rgb.device)
         self._ready.add(key)
@@ -64,12 +78,13 @@ class RoundTripPipeline:
         the slot's stream current.  sink(job_index, slot, stream, x_r, x_d): optional consumer of the
         reconstruction, enqueued on the decoder's stream right after the decode (the buffers are
         reused by the slot's next job).  Returns [(job_index, compress_dict, (x_r, x_d))] for the last
-        `keep_last` jobs (default S; their device buffers are still intact when run() returns)."""
+        `keep_last` jobs (default and at most the number of decompress slots; their device buffers are still
+        intact when run() returns)."""
         jobs = list(jobs)
-        keep_last = self.S if keep_last is None else keep_last
+        keep_last = self.D if keep_last is None else keep_last
         if not jobs:
             return []
-        if self.threads and self.S > 1 and len(jobs) > 1:
+        if self.threads and self.S > 1 and self.D == self.S and len(jobs) > 1:
             self._prepare(jobs, stage_input)
             done = self._run_threads(jobs, stage_input, sink)
         else:
@@ -115,16 +130,17 @@ class RoundTripPipeline:
         return done
 
     def _run_serial(self, jobs, stage_input, sink):
-        net, S = self.net, self.S
+        net, S, D = self.net, self.S, self.D
         enc, dec = deque(), deque()
         done = []
 
         def finish_encode():
             j, slot, h = enc.popleft()
             c = h.result()
-            if len(dec) == S:           # the decoder slot of this job is still busy with job j - S
+            if len(dec) == D:           # the decoder slot of this job is still busy with job j - D
                 self._finish_decode(dec.popleft(), sink, done)
-            dec.append((j, slot, c, net.decompress_async(c["r_strings"], c["d_strings"], c["shape"], slot=S + slot)))
+            dslot = j % D
+            dec.append((j, dslot, c, net.decompress_async(c["r_strings"], c["d_strings"], c["shape"], slot=S + dslot)))
 
         for n, job in enumerate(jobs):
             slot = n % S
