@@ -27,6 +27,7 @@ def _source_hash():
     for d in deps:
         h.update(os.path.basename(d).encode())
         h.update(open(d, "rb").read())
+    h.update(os.environ.get("RGBD_BUILD_DEFINES", "").encode())
     return h.hexdigest()
 
 
@@ -50,7 +51,8 @@ def build(force=False, verbose=False):
             continue
         obj = os.path.join(objdir, src.rsplit(".", 1)[0] + ".o")
         objs.append(obj)
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        extra = os.environ.get("RGBD_BUILD_DEFINES", "").split()     # e.g. -DRGBD_TIMING_PROBES for scratch/ experiments
+        cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()

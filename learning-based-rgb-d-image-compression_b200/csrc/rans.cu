@@ -417,12 +417,15 @@ size_t cdf_smem_bytes(const rgbd_rans_tables *t) {
 
 }  // namespace
 
-// timing experiments only (scratch/skip_probe.py): RGBD_RANS_SKIP=1 drops the coder kernels, =2 replaces them by a
-// one-warp kernel that only waits as long as the coder would (its latency without its shared memory / SM footprint)
+#ifdef RGBD_TIMING_PROBES
+// Timing experiments only (scratch/skip_probe.py; NOT compiled into the shipped library — build with
+// RGBD_BUILD_DEFINES=-DRGBD_TIMING_PROBES): RGBD_RANS_SKIP=1 drops the coder kernels, =2 replaces them by a one-warp
+// kernel that only waits as long as the coder would (its latency without its shared memory / SM footprint).
 __global__ void rans_sleep_kernel(long long ns) {
     const long long t0 = clock64();
     while (clock64() - t0 < ns * 19 / 10) __nanosleep(2000);
 }
+#endif
 
 extern "C" int rgbd_rans_encode(const int32_t *sym, const uint8_t *idx, int64_t stream_stride,
                                 int32_t n_sym, int32_t n_streams, const rgbd_rans_tables *t,
@@ -432,10 +435,12 @@ extern "C" int rgbd_rans_encode(const int32_t *sym, const uint8_t *idx, int64_t 
     RGBD_CHECK_ARG(t->n_tables > 0 && t->n_tables <= kMaxTables, "n_tables must be in 1..256");
     RGBD_CHECK_ARG(t->enc_rec != nullptr, "tables have no encoder records (enc_rec)");
     if (n_streams == 0) return RGBD_OK;
+#ifdef RGBD_TIMING_PROBES
     if (getenv("RGBD_RANS_SKIP")) {
         if (atoi(getenv("RGBD_RANS_SKIP")) == 2) rans_sleep_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((long long)n_sym * 74);
         return RGBD_OK;
     }
+#endif
     const int grid = (n_streams + kWarpsPerBlock - 1) / kWarpsPerBlock;
     rans_encode_kernel<<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
         sym, idx, stream_stride, n_sym, n_streams, *t, out, cap_words, nwords);
@@ -464,10 +469,12 @@ extern "C" int rgbd_rans_decode_chunk(const uint32_t *words, const int64_t *word
     const size_t smem = cdf_smem_bytes(t);
     RGBD_CHECK_ARG(smem <= 200 * 1024, "CDF tables do not fit in shared memory");
     if (n_streams == 0 || n_sym == 0) return RGBD_OK;
+#ifdef RGBD_TIMING_PROBES
     if (getenv("RGBD_RANS_SKIP")) {
         if (atoi(getenv("RGBD_RANS_SKIP")) == 2) rans_sleep_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((long long)n_sym * 150);
         return RGBD_OK;
     }
+#endif
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(rans_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

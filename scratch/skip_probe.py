@@ -1,6 +1,7 @@
 """Timing experiment: pipelined throughput with the rANS kernels skipped (after one real warm-up step so every buffer
 holds plausible data) = what the conv pipeline alone sustains; the difference to the real run is what the coder's
-serial chains / SM fencing cost."""
+serial chains / SM fencing cost.
+Needs a library built with the probes: RGBD_BUILD_DEFINES=-DRGBD_TIMING_PROBES python <pkg>/build.py --force"""
 import os, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -50,6 +50,59 @@ def test_launch_decomposition_equals_torch(mod):
     assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
 
 
+def test_fused_parity_deconv_weights_equal_torch():
+    """ConvTranspose2d(5, 2, 2, output_padding=1) with <= 4 output channels as ONE 3x3 conv over the input lattice
+    whose 16 columns are (output parity, channel) + a pixel shuffle (RGBD_EPI_SHUFFLE2): emulated in torch."""
+    torch.manual_seed(1)
+    for cout in (3, 1):
+        mod = nn.ConvTranspose2d(6, cout, 5, 2, padding=2, output_padding=1)
+        pc = PackedConv(mod, "cpu")
+        w = pc.wtc_shuffle.float()                       # [9 taps][16 cols][cin_pad]
+        x = torch.randn(2, 6, 7, 9).bfloat16().float()
+        xh = x.permute(0, 2, 3, 1)
+        N, H, W, Cin = xh.shape
+        acc = torch.zeros(N, H, W, 16)
+        for u, (dy, dx) in enumerate((a, b) for a in (-1, 0, 1) for b in (-1, 0, 1)):
+            iy, ix = torch.arange(H) + dy, torch.arange(W) + dx
+            vy, vx = (iy >= 0) & (iy < H), (ix >= 0) & (ix < W)
+            g = xh[:, iy.clamp(0, H - 1)][:, :, ix.clamp(0, W - 1)] * (vy[:, None] & vx[None, :])[None, :, :, None]
+            acc += g @ w[u, :, :Cin].t()
+        y = torch.zeros(N, 2 * H, 2 * W, cout)
+        for q in range(4):
+            y[:, (q >> 1)::2, (q & 1)::2] = acc[..., 4 * q:4 * q + cout] + mod.bias
+        with torch.no_grad():
+            m2 = nn.ConvTranspose2d(6, cout, 5, 2, padding=2, output_padding=1)
+            m2.weight.copy_(mod.weight.bfloat16().float())
+            m2.bias.copy_(mod.bias)
+            want = m2(x)
+        assert torch.allclose(y.permute(0, 3, 1, 2), want, atol=1e-4, rtol=1e-4)
+
+
+def test_space_to_depth_first_layer_equals_torch():
+    """Conv2d(k5, s2, p2) over an image == the packed 3x3 s1 conv over its space-to-depth map (split3 = 2 layout:
+    channel block 2*ry+rx of [hi | lo | hi]); here with lo = 0, hi = x to check the tap / channel bookkeeping."""
+    torch.manual_seed(2)
+    for cin in (3, 1):
+        mod = nn.Conv2d(cin, 8, 5, 2, 2)
+        pc = PackedConv(mod, "cpu", split3=True, s2d=True)
+        assert (pc.k, pc.stride, pc.pad, pc.Cin, pc.flop_taps) == (3, 1, 1, 12 * cin, 25)
+        x = torch.randn(2, cin, 8, 12)
+        hi = x.bfloat16().float()
+        lo = x - hi
+        # [N, H/2, W/2, 4 blocks x (hi | lo | hi)]
+        blocks = []
+        for ry in range(2):
+            for rx in range(2):
+                blocks += [hi[:, :, ry::2, rx::2], lo[:, :, ry::2, rx::2], hi[:, :, ry::2, rx::2]]
+        s2d = torch.cat(blocks, dim=1).permute(0, 2, 3, 1).contiguous()
+        got = emulate(pc, s2d).permute(0, 3, 1, 2)
+        with torch.no_grad():
+            want = mod(x)
+        # hi*w_hi + lo*w_hi + hi*w_lo = x*w - lo*w_lo: the dropped term is ~2^-16 relative
+        assert got.shape == want.shape
+        assert torch.allclose(got, want, atol=2e-4, rtol=1e-4)
+
+
 def test_deconv_phase_flops_equal_dense_count():
     pc = PackedConv(nn.ConvTranspose2d(4, 4, 5, 2, padding=2, output_padding=1), "cpu")
     _, _, launches = pc.launches(8, 8)
