@@ -12,6 +12,7 @@ that is the codec's API contract (they are the compressed file).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -128,15 +129,26 @@ def cpu_arm(args, pairs, steps, warmup):
     orc = OracleCodec(net.state_dict(), use_ref_coder=use_ref)
     rgb, depth = make_inputs(pairs, args.height, args.width, seed=1234)
     times = []
+    sample = []      # per pair: stream bytes and PSNR of the CPU path (the parity reference of the GPU line)
+    H, W = args.height, args.width
     for it in range(warmup + steps):
         t0 = time.perf_counter()
+        outs = []
         for i in range(pairs):
             c = orc.compress(rgb[i:i + 1], depth[i:i + 1])
-            orc.decompress(c["r_strings"], c["d_strings"], c["shape"])
+            outs.append((c, orc.decompress(c["r_strings"], c["d_strings"], c["shape"])))
         if it >= warmup:
             times.append(time.perf_counter() - t0)
+        if not sample:
+            for i, (c, r) in enumerate(outs):
+                row = {}
+                for key, m, x in (("r_strings", "r", rgb), ("d_strings", "d", depth)):
+                    row["bytes_" + m] = sum(len(s_) for grp in c[key] for s_ in grp)
+                    mse = float(((r["x_hat"][m][:, :, :H, :W].double() - x[i:i + 1, :, :H, :W].double()) ** 2).mean())
+                    row["psnr_" + m] = 99.0 if mse <= 0 else 10 * math.log10(1.0 / mse)
+                sample.append(row)
     total = sum(times)
-    return {"value": pairs * len(times) / total, "unit": UNIT, "cores": torch.get_num_threads(),
+    return {"pairs_coded": sample, "value": pairs * len(times) / total, "unit": UNIT, "cores": torch.get_num_threads(),
             "kind": "port", "coder": "reference ans (oracle/_ref)" if use_ref else "C restatement",
             "sample": f"{pairs} pair(s) x {len(times)} timed pass(es) of {args.height}x{args.width} "
                       f"compress+decompress, batch 1, torch CPU fp32 ({warmup} warm-up)",
@@ -294,7 +306,27 @@ def run_b200(args):
             "quality": stats,
         }
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = {k: v for k, v in cpu_arm(args, args.cpu_pairs, 1, 0).items()}
+            cb = cpu_arm(args, args.cpu_pairs, 1, 0)
+            coded = cb.pop("pairs_coded")
+            line["cpu_baseline"] = cb
+            # correctness gate next to the throughput number: the same pairs through the CPU path (fp32
+            # restatement of the reference) and through this GPU run — bpp deviation and PSNR deviation per modality
+            first = [e for e in res2 if e[0] % S == 0]     # slot 0 = pairs 0..B-1 of this rank (most recent run)
+            if first and rank == 0:
+                _, c0, (xr, xd) = first[-1]
+                npx = args.height * args.width
+                dev_bpp, dev_psnr = [], []
+                for i, row in enumerate(coded[:B]):
+                    for key, m, x, xh in (("r_strings", "r", rgb_d, xr), ("d_strings", "d", depth_d, xd)):
+                        nbytes = sum(len(grp[i]) for grp in c0[key])
+                        dev_bpp.append(100.0 * abs(nbytes - row["bytes_" + m]) / row["bytes_" + m])
+                        mse = float(((xh[i:i + 1, :, :args.height, :args.width].double() -
+                                      x[i:i + 1, :, :args.height, :args.width].double()) ** 2).mean())
+                        psnr = 99.0 if mse <= 0 else 10 * math.log10(1.0 / mse)
+                        dev_psnr.append(abs(psnr - row["psnr_" + m]))
+                line["parity_vs_cpu_path"] = {"pairs": len(coded[:B]), "max_bpp_dev_pct": round(max(dev_bpp), 4),
+                                              "max_psnr_dev_db": round(max(dev_psnr), 5),
+                                              "tolerance": "bpp 0.5 %, PSNR 0.05 dB (BASELINE north_star, bf16 mode)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
