@@ -302,6 +302,8 @@ def run_b200(args):
                          "frac": roof["tflops"] / tens_peak, "traffic": None,
                          "kernel": roof["kernel"], "launches": roof["launches"], "peak_source": pk_src + " bf16 sustained",
                          "share_of_step": S * roof["ms"] / (ms / K), "algorithmic_gflop_per_pair": GFLOP_PER_PAIR, "by_class": roof["by_class"],
+                         "timing": "CUDA events around every run of consecutive conv launches of one compress + decompress plan",
+                         "achieved_with_per_launch_events": roof["per_launch_events_tflops"],
                          "whole_step_tflops": GFLOP_PER_PAIR * pairs_per_step * K / ms},
             "quality": stats,
         }
@@ -366,8 +368,36 @@ def conv_roofline(net, B, Hp, Wp, dev, dec_slot=0):
                 c[3] += 1
             total_flops += prog.flops
             n += len(evs)
+    # Second pass: one event pair around every maximal RUN of consecutive conv launches instead of around every launch.
+    # Per-launch events put ~10 us of bubble around each of the ~640 launches (the kernels measure 10+ us shorter under
+    # ncu) and forbid the programmatic-dependent-launch overlap the real run has; per-run events keep launch gaps and
+    # PDL exactly as in production.  `achieved` uses this pass; the per-launch pass feeds the by-class split.
+    run_ms = 0.0
+    with torch.cuda.device(dev):
+        for prog in (net._program("encoder", B, Hp, Wp),
+                     net._program("decoder", B, Hp // 64, Wp // 64, slot=dec_slot)):
+            sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            evs, open_ev = [], None
+            for op in prog.ops:
+                is_conv = getattr(op, "is_conv", False)
+                if is_conv and open_ev is None:
+                    open_ev = torch.cuda.Event(enable_timing=True)
+                    open_ev.record()
+                if not is_conv and open_ev is not None:
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record()
+                    evs.append((open_ev, e))
+                    open_ev = None
+                op(sp)
+            if open_ev is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                evs.append((open_ev, e))
+            torch.cuda.synchronize(dev)
+            run_ms += sum(a.elapsed_time(b) for a, b in evs)
     by_class = {
         "ridge_flop_per_byte": round(ridge, 1),
+        "timing": "one CUDA-event pair per launch (adds ~10 us of bubble per launch)",
         "tensor_bound_launches": {"launches": cls["tensor"][3], "ms": round(cls["tensor"][0], 3),
                                   "tflops": round(cls["tensor"][1] / max(1e-9, cls["tensor"][0]) / 1e9, 1),
                                   "frac_of_bf16_peak": round(cls["tensor"][1] / max(1e-9, cls["tensor"][0]) / 1e9 / pk["bf16_tflops_sustained"], 3)},
@@ -375,7 +405,8 @@ def conv_roofline(net, B, Hp, Wp, dev, dec_slot=0):
                                "gbs": round(cls["hbm"][2] / max(1e-9, cls["hbm"][0]) / 1e6, 1),
                                "frac_of_hbm_peak": round(cls["hbm"][2] / max(1e-9, cls["hbm"][0]) / 1e6 / pk["hbm_gbs"], 3)},
     }
-    return {"tflops": total_flops / (total_ms / 1e3) / 1e12, "ms": total_ms, "launches": n, "by_class": by_class,
+    return {"tflops": total_flops / (run_ms / 1e3) / 1e12, "ms": run_ms, "launches": n, "by_class": by_class,
+            "per_launch_events_tflops": total_flops / (total_ms / 1e3) / 1e12,
             "kernel": "conv_simt_kernel" if net.precision == "fp32" else "conv_halo_kernel (tcgen05 implicit GEMM, halo-resident A tiles)"}
 
 
