@@ -192,3 +192,26 @@ def test_model_zoo_lookup_order():
     name = "ELIC_united_R2D_q2"
     hit = next(v for k, v in rgbd_b200.modelZoo.items() if name.find(k) != -1)
     assert hit is rgbd_b200.ELIC_united_R2D
+
+
+def test_plan_arena_reuses_and_coalesces_storage():
+    """Builder.alloc / release: a small heap over the plan's byte arena (engine.py) — released ranges are reused by
+    later tensors of any shape, neighbours coalesce, two views of one buffer release it once."""
+    from rgbd_b200.engine import Builder, View
+    b = Builder(torch.device("cpu"), torch.bfloat16, tensor_cores=False)
+    a = b.alloc(1, 8, 8, 16)                      # 2 KB inside a fresh 64 MB chunk
+    c = b.alloc(1, 8, 8, 32)                      # 4 KB right behind it
+    assert b.prog.bytes == 64 << 20 and len(b.prog.pool["chunks"]) == 1
+    pa, pc_ = a.ptr(), c.ptr()
+    assert pc_ == pa + 2048
+    b.release(a, View(a.buf, 0, 8))               # second view of the same buffer: released once
+    assert b.prog.pool["chunks"][0][1][0] == (0, 2048)
+    d = b.alloc(1, 4, 4, 16, torch.float32)       # 1 KB fp32 tensor reuses the head of the freed range
+    assert d.ptr() == pa and d.dtype == torch.float32 and d.cstride == 16
+    b.release(c, d)
+    # everything free again and coalesced into one range
+    assert b.prog.pool["chunks"][0][1] == [(0, 64 << 20)]
+    e = b.alloc(1, 16, 16, 24)                    # bf16 rows padded to 8 channels: 24 -> 24, 12 KB
+    assert e.ptr() == pa and e.cstride == 24 and b.prog.bytes == 64 << 20
+    z = b.alloc(1, 8, 8, 16, zero=True)           # zero-initialised buffers get a private, exact chunk
+    assert len(b.prog.pool["chunks"]) == 2 and float(z.buf.float().abs().sum()) == 0.0
