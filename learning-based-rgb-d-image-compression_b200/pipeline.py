@@ -15,6 +15,7 @@ and the ctypes launches release the GIL.
 Images are independent; nothing here changes what any single compress() /
 decompress() call computes or the bytes it produces.
 """
+import contextlib
 import threading
 from collections import deque
 
@@ -104,7 +105,8 @@ class RoundTripPipeline:
 
         def worker(slot):
             try:
-                with torch.cuda.device(device), torch.no_grad():
+                on_dev = torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()
+                with on_dev, torch.no_grad():
                     mine, prev = [], None
                     for n in range(slot, len(jobs), S):
                         rgb, depth = self._input(n, slot, jobs[n], stage_input)
