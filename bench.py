@@ -188,46 +188,83 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch or (2 if args.precision == "fp32" else 24)
-
     net = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4, precision=args.precision).eval()
     net.load_state_dict(rgbd_b200.synthetic.synthetic_state_dict(net, 0, args.preset))
     net.update(force=True)
     net = net.to(dev)
     net.use_cuda_graph = bool(args.graphs)
-    # each rank owns its contiguous shard of the global batch (weak scaling: S x B pairs per GPU and
-    # step); S batches are in flight on S CUDA streams so that the serial rANS kernels of one batch
-    # overlap the convolutions of the others
-    S = max(1, args.slots)
-    rgb_h, depth_h = make_inputs(S * B, args.height, args.width, seed=1234 + rank * S * B)
-    rgb_h, depth_h = rgb_h.pin_memory(), depth_h.pin_memory()
-    rgb_d, depth_d = rgb_h.to(dev), depth_h.to(dev)
-    Hp, Wp = rgb_h.shape[-2:]
-    sl = [slice(i * B, (i + 1) * B) for i in range(S)]
-    host_out = [(torch.empty((B, 3, Hp, Wp)).pin_memory(), torch.empty((B, 1, Hp, Wp)).pin_memory()) for _ in range(max(S, args.dec_slots or S))]
 
-    # Round-trip pipeline (rgbd_b200.pipeline): S compress jobs and S decompress jobs in flight, each on
-    # its own stream + launch plan, so the decoder's serial rANS chain of batch k hides behind the
-    # convolutions of batches k+1..; one step = S batches of B pairs, every pair compressed AND
-    # decompressed inside the timed region.
-    from rgbd_b200.pipeline import RoundTripPipeline
-    pipe = RoundTripPipeline(net, S, threads=bool(args.threads), high_priority_decode=bool(args.hiprio), dec_slots=args.dec_slots or None)
+    def prepare(B):
+        """Inputs, pinned host buffers, the pipeline and its 2S launch plans for B pairs per job (warm-up included:
+        building the plans is what allocates the HBM)."""
+        # each rank owns its contiguous shard of the global batch (weak scaling: S x B pairs per GPU and
+        # step); S batches are in flight on S CUDA streams so that the serial rANS kernels of one batch
+        # overlap the convolutions of the others
+        S = max(1, args.slots)
+        rgb_h, depth_h = make_inputs(S * B, args.height, args.width, seed=1234 + rank * S * B)
+        rgb_h, depth_h = rgb_h.pin_memory(), depth_h.pin_memory()
+        rgb_d, depth_d = rgb_h.to(dev), depth_h.to(dev)
+        Hp, Wp = rgb_h.shape[-2:]
+        sl = [slice(i * B, (i + 1) * B) for i in range(S)]
+        host_out = [(torch.empty((B, 3, Hp, Wp)).pin_memory(), torch.empty((B, 1, Hp, Wp)).pin_memory()) for _ in range(max(S, args.dec_slots or S))]
 
-    def steps_device(k):
-        jobs = [(rgb_d[sl[i % S]], depth_d[sl[i % S]]) for i in range(k * S)]
-        return pipe.run(jobs)
+        # Round-trip pipeline (rgbd_b200.pipeline): S compress jobs and S decompress jobs in flight, each on
+        # its own stream + launch plan, so the decoder's serial rANS chain of batch k hides behind the
+        # convolutions of batches k+1..; one step = S batches of B pairs, every pair compressed AND
+        # decompressed inside the timed region.
+        from rgbd_b200.pipeline import RoundTripPipeline
+        pipe = RoundTripPipeline(net, S, threads=bool(args.threads), high_priority_decode=bool(args.hiprio), dec_slots=args.dec_slots or None)
 
-    def steps_e2e(k):
-        def stage_input(j, slot, stream):    # H2D of this batch's images from pinned host memory
-            return rgb_h[sl[slot]].to(dev, non_blocking=True), depth_h[sl[slot]].to(dev, non_blocking=True)
+        def steps_device(k):
+            jobs = [(rgb_d[sl[i % S]], depth_d[sl[i % S]]) for i in range(k * S)]
+            return pipe.run(jobs)
 
-        def sink(j, slot, stream, x_r, x_d):  # D2H of the reconstruction into pinned host buffers
-            host_out[slot][0].copy_(x_r, non_blocking=True)
-            host_out[slot][1].copy_(x_d, non_blocking=True)
+        def steps_e2e(k):
+            def stage_input(j, slot, stream):    # H2D of this batch's images from pinned host memory
+                return rgb_h[sl[slot]].to(dev, non_blocking=True), depth_h[sl[slot]].to(dev, non_blocking=True)
 
-        res = pipe.run([None] * (k * S), stage_input=stage_input, sink=sink)
-        torch.cuda.synchronize(dev)
-        return res
+            def sink(j, slot, stream, x_r, x_d):  # D2H of the reconstruction into pinned host buffers
+                host_out[slot][0].copy_(x_r, non_blocking=True)
+                host_out[slot][1].copy_(x_d, non_blocking=True)
+
+            res = pipe.run([None] * (k * S), stage_input=stage_input, sink=sink)
+            torch.cuda.synchronize(dev)
+            return res
+        W_ = max(3, args.warmup)
+        if os.environ.get("RGBD_BENCH_FAKE_OOM") and B == int(os.environ["RGBD_BENCH_FAKE_OOM"]):
+            raise torch.OutOfMemoryError("fake OOM (test hook)")
+        steps_device(W_)
+        steps_e2e(1)
+        import types
+        return types.SimpleNamespace(**{k: v for k, v in locals().items() if k != "types"})
+
+    # pairs per job: as many as fit.  Plans for 8 + 8 jobs of 24 pairs take ~107 GB of the 180 GB; if building them
+    # runs out of memory on this GPU (every rank must agree), fall back to a smaller job instead of failing the run.
+    candidates = [args.batch] if args.batch else ([2] if args.precision == "fp32" else [24, 16, 8])
+    ns = None
+    for B in candidates:
+        ok = 1
+        try:
+            ns = prepare(B)
+        except torch.OutOfMemoryError as e:
+            ok, ns = 0, None
+            print(f"[bench] rank {rank}: {B} pairs per job do not fit ({str(e)[:80]}...)", file=sys.stderr, flush=True)
+        if world > 1:
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if ok:
+            break
+        ns = None
+        net._invalidate()
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+    if ns is None:
+        raise SystemExit("bench: no job size fits this GPU")
+    S, rgb_h, depth_h, rgb_d, depth_d, Hp, Wp, sl, host_out = (ns.S, ns.rgb_h, ns.depth_h, ns.rgb_d, ns.depth_d, ns.Hp,
+                                                               ns.Wp, ns.sl, ns.host_out)
+    pipe, steps_device, steps_e2e = ns.pipe, ns.steps_device, ns.steps_e2e
 
     def barrier():
         if world > 1:
@@ -246,8 +283,7 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), out
 
-    W_, K = max(3, args.warmup), max(1, args.steps)
-    steps_device(W_)
+    W_, K = max(3, args.warmup), max(1, args.steps)   # (the W_ warm-up steps ran inside prepare())
     # L2 note: one step streams > 1 GB of activations per image through HBM, far beyond the 126 MB L2,
     # so consecutive steps cannot serve each other from cache (no explicit flush needed).
     L.load().rgbd_launch_count(1)
@@ -268,7 +304,6 @@ def run_b200(args):
                        rgb_d[sl[slot]][:, :, :args.height, :args.width], depth_d[sl[slot]][:, :, :args.height, :args.width],
                        outs[i][0][:, :, :args.height, :args.width], outs[i][1][:, :, :args.height, :args.width])
 
-    steps_e2e(1)
     ms_e2e, res2 = timed(steps_e2e, K)
     cs2 = [c for _, c, _ in res2]
     outs2 = [xs for _, _, xs in res2]
