@@ -281,3 +281,21 @@ def test_cuda_graph_replay_gives_the_same_bytes():
         assert L.load().rgbd_launch_count(0) > 500     # replays report their kernel nodes
         assert g["r_strings"] == eager["r_strings"] and g["d_strings"] == eager["d_strings"]
         assert torch.equal(rec_g["x_hat"]["r"], rec_e["x_hat"]["r"]) and torch.equal(rec_g["x_hat"]["d"], rec_e["x_hat"]["d"])
+
+
+def test_container_files_roundtrip_through_the_codec(tmp_path):
+    """compress -> the reference's on-disk container (bitstream_io) -> decompress == decompress of the in-memory dict."""
+    from gpu_utils import make_model
+    from rgbd_b200 import bitstream_io as bio
+    net, _ = make_model(rgbd_b200.ELIC_united, "mid", 0, precision="bf16")
+    rgb, depth = synthetic_pairs(1, 120, 150, seed=3)
+    rgb_p, depth_p = pad_to_multiple(rgb), pad_to_multiple(depth)
+    out = net.compress(rgb_p.to(DEV), depth_p.to(DEV))
+    rp, dp = str(tmp_path / "rgb" / "x.bin"), str(tmp_path / "depth" / "x.bin")
+    bpp_r, bpp_d = bio.save_compressed(out, (120, 150), rp, dp)
+    assert bpp_r > 0 and bpp_d > 0
+    rs, ds, shape, hw = bio.load_compressed(rp, dp)
+    assert hw == (120, 150) and tuple(shape) == tuple(out["shape"])
+    a = net.decompress(out["r_strings"], out["d_strings"], out["shape"])
+    b = net.decompress(rs, ds, shape)
+    assert torch.equal(a["x_hat"]["r"], b["x_hat"]["r"]) and torch.equal(a["x_hat"]["d"], b["x_hat"]["d"])
