@@ -1163,13 +1163,17 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
                8 * (2 * kMaxA + 2 * kMaxB + 12 + 2 * kTileQ) + 16 + 128 + 4 * (size_t)d->cout_pad + 64 + (p.stage_epi ? kStageBytes : 0) +
                (p.mul_blocks ? 1024 + 2 * (size_t)p.mul_blocks * p.mul_bytes : 0);
     if (pl->smem < (size_t)kMinSmem) pl->smem = kMinSmem;
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
-            num_sms = 148;
+    // per-device state (one process may hold nets on several GPUs; function attributes are per device)
+    static int sms_of[64] = {};
+    static bool configured_on[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
+    if (sms_of[dev] == 0) {
+        if (cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms_of[dev] <= 0)
+            sms_of[dev] = 148;
     }
+    const int num_sms = sms_of[dev];
     pl->grid = dim3((unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms));
     pl->out_f32 = d->y_dtype == RGBD_DT_F32;
     pl->epi = d->epi;
@@ -1244,8 +1248,7 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
             return rc;
         }
     }
-    static bool configured = false;
-    if (!configured) {
+    if (!configured_on[dev]) {
         const int cap = 227 * 1024;
         cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
@@ -1255,7 +1258,7 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
         cudaFuncSetAttribute(conv_halo_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         cudaFuncSetAttribute(conv_halo_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-        configured = true;
+        configured_on[dev] = true;
     }
     if (getenv("RGBD_TC_VERBOSE"))
         fprintf(stderr, "conv_halo: %dx%d taps %d Cin %d Cout %d | TW %d R %d P %d MT %d box_rows %d groups %d kb %d BN %d nA %d nB %d tps %d a %d b %d res %d tiles %d smem %zu\n",

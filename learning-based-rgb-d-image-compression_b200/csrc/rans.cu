@@ -475,10 +475,13 @@ extern "C" int rgbd_rans_decode_chunk(const uint32_t *words, const int64_t *word
         return RGBD_OK;
     }
 #endif
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[64] = {};   // per device: function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
+    if (smem > configured[dev]) {
         cudaFuncSetAttribute(rans_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+        configured[dev] = smem;
     }
     const int grid = (n_streams + kWarpsPerBlock - 1) / kWarpsPerBlock;
     rans_decode_kernel<<<grid, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
