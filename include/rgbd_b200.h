@@ -248,6 +248,13 @@ int rgbd_rans_encode(const int32_t *sym, const uint8_t *idx, int64_t stream_stri
                      int32_t n_streams, const rgbd_rans_tables *t, uint32_t *out,
                      int64_t cap_words, int32_t *nwords, void *stream);
 
+/* The `bytes` objects compress() returns (models/elic_united.py:423-427: encoder.flush() / RansEncoder strings): packs
+ * the tails of two groups of finished streams (group a: n_a streams of cap_a words in out_a, then group b; nwords in
+ * that order, as written by rgbd_rans_encode) into dst = [n_a + n_b counts | words of stream 0 | stream 1 | ...].
+ * dst may be pinned host memory (zero-copy).  If the words do not fit dst_cap_words only the counts are written. */
+int rgbd_gather_streams(const uint32_t *out_a, int64_t cap_a, int32_t n_a, const uint32_t *out_b, int64_t cap_b,
+                        int32_t n_b, const int32_t *nwords, uint32_t *dst, int64_t dst_cap_words, void *stream);
+
 /* RansDecoder.set_stream (rans_interface.cpp:278-284): state[s] = {x, next word}. */
 typedef struct rgbd_rans_dec_state {
     uint64_t x;

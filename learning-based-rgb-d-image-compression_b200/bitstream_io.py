@@ -44,22 +44,59 @@ def write_modality(fd, orig_hw, shape, strings):
     return n
 
 
+MAX_SIDE = 1 << 16      # largest image side the reader accepts (a corrupt header must not size a launch plan)
+
+
+def _remaining(fd):
+    try:
+        return os.fstat(fd.fileno()).st_size - fd.tell()
+    except (AttributeError, OSError, ValueError):
+        return None     # not a real file (BytesIO ...): the per-read length checks still apply
+
+
 def read_modality(fd):
-    """-> (orig_hw, strings, shape): strings = list (entries) of lists of bytes, shape = (z_H, z_W)."""
+    """-> (orig_hw, strings, shape): strings = list (entries) of lists of bytes, shape = (z_H, z_W).
+    The container itself is generic (any number of entries, like the reference's read_body); every count and
+    length is checked against the bytes that are left before it drives a loop or a read.  What the codec
+    additionally requires of a file is checked by `check_codec_header` (called from `load_compressed`)."""
     orig_hw = _get(fd, 2)
     zh, zw, n_entries = _get(fd, 3)
+    left = _remaining(fd)
+    if left is not None and 4 * n_entries > left:
+        raise ValueError("corrupt bitstream container: entry count exceeds the file")
     strings = []
     for _ in range(n_entries):
         (count,) = _get(fd, 1)
+        left = _remaining(fd)
+        if left is not None and 4 * count > left:
+            raise ValueError("corrupt bitstream container: string count exceeds the file")
         group = []
         for _ in range(count):
             (nbytes,) = _get(fd, 1)
+            left = _remaining(fd)
+            if left is not None and nbytes > left:
+                raise ValueError("truncated bitstream container")
             s = fd.read(nbytes)
             if len(s) != nbytes:
                 raise ValueError("truncated bitstream container")
             group.append(s)
         strings.append(group)
     return tuple(orig_hw), strings, (zh, zw)
+
+
+def check_codec_header(orig_hw, shape, strings):
+    """What ELIC_united.decompress needs of a parsed file before a launch plan is sized from it: two entries (y, z),
+    a sane image size, latent shape = ceil(orig / 64) (dataset/utils.py:58-67 pads to multiples of 64), one z string
+    per image and as many y strings."""
+    if len(strings) != 2:
+        raise ValueError(f"corrupt bitstream container: {len(strings)} entries (expected 2: y, z)")
+    if not (0 < orig_hw[0] <= MAX_SIDE and 0 < orig_hw[1] <= MAX_SIDE):
+        raise ValueError(f"corrupt bitstream container: image size {tuple(orig_hw)}")
+    if tuple(shape) != (-(-orig_hw[0] // 64), -(-orig_hw[1] // 64)):
+        raise ValueError(f"corrupt bitstream container: latent shape {tuple(shape)} does not belong to a "
+                         f"{tuple(orig_hw)} image")
+    if not strings[1] or len(strings[0]) % len(strings[1]):
+        raise ValueError("corrupt bitstream container: y / z string counts do not match")
 
 
 def write_modality_file(path, orig_hw, shape, strings):
@@ -88,4 +125,6 @@ def load_compressed(rgb_path, depth_path):
     hw_d, ds, shape_d = read_modality_file(depth_path)
     if hw_r != hw_d or shape_r != shape_d:
         raise ValueError("rgb and depth containers disagree on the image / latent size")
+    check_codec_header(hw_r, shape_r, rs)
+    check_codec_header(hw_d, shape_d, ds)
     return rs, ds, shape_r, hw_r

@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
             continue
         obj = os.path.join(objdir, src.rsplit(".", 1)[0] + ".o")
         objs.append(obj)
-        extra = os.environ.get("RGBD_BUILD_DEFINES", "").split()     # e.g. -DRGBD_TIMING_PROBES for scratch/ experiments
+        extra = os.environ.get("RGBD_BUILD_DEFINES", "").split()     # e.g. -DRGBD_TIMING_PROBES for profiles/tools/ experiments
         cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:

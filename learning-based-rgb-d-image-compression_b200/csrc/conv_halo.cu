@@ -10,7 +10,7 @@
 //     input — the tile plus its halo — lands in shared memory as consecutive 128-byte rows with the
 //     128-byte swizzle.  Because the swizzle is a function of the absolute shared-memory address, the
 //     A operand of tap (qy, qx) is the SAME halo tile read through a UMMA descriptor whose start
-//     address is shifted by (qy * P + qx) rows (verified on B200: scratch/desc_test.cu).  A k x k
+//     address is shifted by (qy * P + qx) rows (verified on B200: profiles/tools/desc_test.cu).  A k x k
 //     filter therefore fetches its input once instead of k*k times.  Out-of-image rows/columns are
 //     zero-filled by TMA (= the reference's zero padding).  A tap group is the set of taps that read
 //     the same input lattice: one group for stride 1, the four input parity classes for stride 2
@@ -34,6 +34,7 @@
 #include <cuda.h>
 #include <new>
 #include <cstdlib>
+#include <mutex>
 
 namespace {
 
@@ -893,15 +894,19 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// one-time initialisation below is shared by host threads (the round-trip pipeline may drive each slot from its own thread)
+std::mutex g_init_mutex;
+
 EncodeTiledFn get_encode() {
     static EncodeTiledFn fn = nullptr;
-    if (!fn) {
+    static std::once_flag once;
+    std::call_once(once, [] {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
             fn = (EncodeTiledFn)p;
-    }
+    });
     return fn;
 }
 
@@ -941,6 +946,7 @@ const void *identity_ptr() {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_init_mutex);
     if (!ptr[dev]) {
         void *q = nullptr;
         if (cudaGetSymbolAddress(&q, g_identity) != cudaSuccess) return nullptr;
@@ -988,7 +994,10 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     HParams &p = pl->p;
     p.d = *d;
     p.dbg = nullptr;
+#ifdef RGBD_TIMING_PROBES
+    // development builds only (RGBD_BUILD_DEFINES=-DRGBD_TIMING_PROBES): cycle counters of CTA 0 go to this device pointer
     if (const char *e = getenv("RGBD_TC_TRACE")) p.dbg = (long long *)strtoull(e, nullptr, 0);
+#endif
 
     // ---- tap groups: taps that read the same input lattice (parity class when i_step == 2) ----
     const int st = d->i_step;
@@ -1169,11 +1178,15 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
     int dev = 0;
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
-    if (sms_of[dev] == 0) {
-        if (cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms_of[dev] <= 0)
-            sms_of[dev] = 148;
+    int num_sms;
+    {
+        std::lock_guard<std::mutex> lock(g_init_mutex);
+        if (sms_of[dev] == 0) {
+            if (cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms_of[dev] <= 0)
+                sms_of[dev] = 148;
+        }
+        num_sms = sms_of[dev];
     }
-    const int num_sms = sms_of[dev];
     pl->grid = dim3((unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms));
     pl->out_f32 = d->y_dtype == RGBD_DT_F32;
     pl->epi = d->epi;
@@ -1248,6 +1261,7 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
             return rc;
         }
     }
+    std::unique_lock<std::mutex> init_lock(g_init_mutex);
     if (!configured_on[dev]) {
         const int cap = 227 * 1024;
         cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
@@ -1260,6 +1274,7 @@ extern "C" int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad
         cudaFuncSetAttribute(conv_halo_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
         configured_on[dev] = true;
     }
+    init_lock.unlock();
     if (getenv("RGBD_TC_VERBOSE"))
         fprintf(stderr, "conv_halo: %dx%d taps %d Cin %d Cout %d | TW %d R %d P %d MT %d box_rows %d groups %d kb %d BN %d nA %d nB %d tps %d a %d b %d res %d tiles %d smem %zu\n",
                 d->Hs, d->Ws, d->ntaps, d->Cin, d->Cout, p.TW, p.R, p.P, p.MT, p.box_rows, p.ngroups, p.kblocks, p.BN, p.nA, p.nB, p.tps,

@@ -18,6 +18,7 @@
 // memory for the whole decode kernel.
 #include "common.cuh"
 #include <cstdlib>
+#include <mutex>
 
 namespace {
 
@@ -411,6 +412,40 @@ __global__ void rans_decode_init_kernel(const uint32_t *__restrict__ words,
     state[s].pos = 2;
 }
 
+// Packs the tails of finished encoder streams into one buffer: dst = [n_total counts | words of stream 0 | stream 1 | ...].
+// `dst` is normally pinned host memory (zero-copy stores): the compressed strings are on the host when the kernel ends.
+__global__ void __launch_bounds__(256)
+gather_streams_kernel(const uint32_t *__restrict__ a, int64_t a_cap, int32_t a_n, const uint32_t *__restrict__ b,
+                      int64_t b_cap, int32_t b_n, const int32_t *__restrict__ nwords, uint32_t *__restrict__ dst,
+                      int64_t dst_cap) {
+    const int s = blockIdx.x, total = a_n + b_n;
+    __shared__ int64_t s_off, s_all;
+    if (threadIdx.x < 32) {
+        int64_t before = 0, all = 0;
+        for (int i = threadIdx.x; i < total; i += 32) {
+            const int32_t n = nwords[i];
+            const int64_t v = n > 0 ? n : 0;
+            all += v;
+            if (i < s) before += v;
+        }
+        for (int o = 16; o; o >>= 1) {
+            before += __shfl_xor_sync(kFull, before, o);
+            all += __shfl_xor_sync(kFull, all, o);
+        }
+        if (threadIdx.x == 0) {
+            s_off = before;
+            s_all = all;
+        }
+    }
+    __syncthreads();
+    const int32_t n = nwords[s];
+    if (threadIdx.x == 0) dst[s] = (uint32_t)n;
+    if (n <= 0 || s_all > dst_cap) return;   // overflowed stream, or the packed buffer is too small (the host falls back)
+    const uint32_t *src = s < a_n ? a + (int64_t)s * a_cap + (a_cap - n) : b + (int64_t)(s - a_n) * b_cap + (b_cap - n);
+    uint32_t *out = dst + total + s_off;
+    for (int32_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = src[i];
+}
+
 size_t cdf_smem_bytes(const rgbd_rans_tables *t) {
     return (((size_t)t->total * 2 + 15) & ~(size_t)15) + 128;   // + slack for the 2-entry window prefetch
 }
@@ -418,7 +453,7 @@ size_t cdf_smem_bytes(const rgbd_rans_tables *t) {
 }  // namespace
 
 #ifdef RGBD_TIMING_PROBES
-// Timing experiments only (scratch/skip_probe.py; NOT compiled into the shipped library — build with
+// Timing experiments only (profiles/tools/skip_probe.py; NOT compiled into the shipped library — build with
 // RGBD_BUILD_DEFINES=-DRGBD_TIMING_PROBES): RGBD_RANS_SKIP=1 drops the coder kernels, =2 replaces them by a one-warp
 // kernel that only waits as long as the coder would (its latency without its shared memory / SM footprint).
 __global__ void rans_sleep_kernel(long long ns) {
@@ -479,13 +514,29 @@ extern "C" int rgbd_rans_decode_chunk(const uint32_t *words, const int64_t *word
     int dev = 0;
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
-    if (smem > configured[dev]) {
-        cudaFuncSetAttribute(rans_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured[dev] = smem;
+    {
+        static std::mutex mu;     // several host threads may drive pipeline slots
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > configured[dev]) {
+            cudaFuncSetAttribute(rans_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured[dev] = smem;
+        }
     }
     const int grid = (n_streams + kWarpsPerBlock - 1) / kWarpsPerBlock;
     rans_decode_kernel<<<grid, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
         words, word_off, word_len, n_streams, state, idx, sym, stream_stride, chunk_off, n_sym, *t);
+    RGBD_LAUNCH_CHECK();
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_gather_streams(const uint32_t *out_a, int64_t cap_a, int32_t n_a, const uint32_t *out_b,
+                                   int64_t cap_b, int32_t n_b, const int32_t *nwords, uint32_t *dst,
+                                   int64_t dst_cap_words, void *stream) {
+    RGBD_CHECK_ARG(nwords && dst && (n_a == 0 || out_a) && (n_b == 0 || out_b), "null pointer");
+    RGBD_CHECK_ARG(n_a >= 0 && n_b >= 0 && cap_a >= 0 && cap_b >= 0 && dst_cap_words >= 0, "sizes");
+    if (n_a + n_b == 0) return RGBD_OK;
+    gather_streams_kernel<<<n_a + n_b, 256, 0, (cudaStream_t)stream>>>(out_a, cap_a, n_a, out_b, cap_b, n_b, nwords, dst,
+                                                                      dst_cap_words);
     RGBD_LAUNCH_CHECK();
     return RGBD_OK;
 }

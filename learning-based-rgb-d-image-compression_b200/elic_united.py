@@ -112,9 +112,11 @@ class ELIC_united(nn.Module):
         self._invalidate()
         return (r & d) | eb
 
-    def load_state_dict(self, state_dict, strict=True):
+    def load_state_dict(self, state_dict, strict=False):
         """Resizes the CDF buffers to the checkpoint's sizes first (models/elic_united.py:588-620,
-        utils/moduleFunc.py:42-88), then a normal strict load."""
+        utils/moduleFunc.py:42-88), then loads like the reference: a strict load is tried first; when it
+        fails and the caller did not ask for strict=True, the mismatch is reported and a non-strict load
+        follows (the reference's fallback branch, :612-620)."""
         for name in ("rgb_gaussian_conditional", "depth_gaussian_conditional", "rgb_entropy_bottleneck",
                      "depth_entropy_bottleneck"):
             mod = getattr(self, name)
@@ -128,7 +130,13 @@ class ELIC_united(nn.Module):
                     if cur.numel() == 0 or cur.shape != state_dict[key].shape:
                         setattr(mod, b, torch.empty(state_dict[key].shape, dtype=cur.dtype, device=cur.device))
             mod.invalidate()
-        rv = super().load_state_dict(state_dict, strict=strict)
+        try:
+            rv = super().load_state_dict(state_dict, strict=True)
+        except RuntimeError as e:
+            if strict:
+                raise
+            print("ELIC_united load state dict strict error:", str(e).splitlines()[0])
+            rv = super().load_state_dict(state_dict, strict=False)
         self._invalidate()
         return rv
 
@@ -141,6 +149,7 @@ class ELIC_united(nn.Module):
         self._packed = None
         self._programs = {}
         self._aux = {}
+        self.__dict__.pop("_slot_streams", None)   # streams belong to the device the module lived on
         for m in (self.rgb_gaussian_conditional, self.depth_gaussian_conditional, self.rgb_entropy_bottleneck,
                   self.depth_entropy_bottleneck):
             m.invalidate()
@@ -375,7 +384,7 @@ class ELIC_united(nn.Module):
             for name, width in ours:
                 idxs.extend(range(start[name], start[name] + width))
             assert len(idxs) == q
-            return torch.tensor(idxs, dtype=torch.long)
+            return torch.tensor(idxs, dtype=torch.long, device="cpu")
 
         base = [("hyper_r", 2 * M), ("hyper_d", 2 * M)] + ([("ch_r", 2 * g), ("ch_d", 2 * g)] if has_ch else [])
         lr, ld = ("loc_r", 2 * g), ("loc_d", 2 * g)
@@ -489,6 +498,7 @@ class ELIC_united(nn.Module):
         # ... and as a space-to-depth map (2x2 pixel blocks -> channels), which turns the 5x5 stride-2 first conv
         # into a 3x3 stride-1 conv with a single tap group (one halo load per tile instead of four parity loads)
         split = 2 if b.tensor_cores else 0
+        b.stage = "io"
         x_r = b.alloc(B, H // 2, W // 2, 36) if split else b.alloc(B, H, W, 3)
         x_d = b.alloc(B, H // 2, W // 2, 12) if split else b.alloc(B, H, W, 1)
         in_r = b.raw((B, 3, H, W), torch.float32)
@@ -496,9 +506,12 @@ class ELIC_united(nn.Module):
         p.io["rgb"], p.io["depth"] = in_r, in_d
         b.op("rgbd_nchw_to_nhwc", in_r.data_ptr(), x_r.ptr(), _DT[x_r.dtype], B, 3, H, W, x_r.cstride, x_r.coff, split)
         b.op("rgbd_nchw_to_nhwc", in_d.data_ptr(), x_d.ptr(), _DT[x_d.dtype], B, 1, H, W, x_d.cstride, x_d.coff, split)
+        b.stage = "g_a"
         y_r, y_d = self._transform(b, self.g_a.rgb_analysis_transform, self.g_a.depth_analysis_transform,
                                    x_r, x_d, final_dtype=torch.float32)
+        b.stage = "h_a"
         z_r, z_d = self._h_a(b, y_r, y_d)
+        b.stage = "coder"
         return y_r, y_d, z_r, z_d
 
     def _tables(self, which_model, which):
@@ -520,18 +533,22 @@ class ELIC_united(nn.Module):
         st = {}
         # both modalities' y streams live in one [2B, ...] buffer so one launch can code all of them
         ycap = ny + ny // 2 + 64
+        zcap = nz + nz // 2 + 64
         ysym_all, yidx_all = b.raw((2 * B, ny), torch.int32), b.raw((2 * B, ny), torch.uint8)
-        yout_all, ynw_all = b.raw((2 * B, ycap), torch.int32), b.raw((2 * B,), torch.int32)
+        yout_all, zout_all = b.raw((2 * B, ycap), torch.int32), b.raw((2 * B, zcap), torch.int32)
+        # word counts of the 4B streams in gather order [y_r | y_d | z_r | z_d] (rgbd_gather_streams)
+        counts = b.raw((4 * B,), torch.int32)
+        ynw_all = counts[:2 * B]
         for k, which in enumerate(("r", "d")):
             eb = self._eb(which)
             med = self._dev32(("med", which), eb.medians)
             s = dict(
                 zsym=b.raw((B, nz), torch.int32), zidx=b.raw((B, nz), torch.uint8),
                 ysym=ysym_all[k * B:(k + 1) * B], yidx=yidx_all[k * B:(k + 1) * B],
-                zcap=nz + nz // 2 + 64, ycap=ycap)
-            s["zout"] = b.raw((B, s["zcap"]), torch.int32)
+                zcap=zcap, ycap=ycap)
+            s["zout"] = zout_all[k * B:(k + 1) * B]
             s["yout"] = yout_all[k * B:(k + 1) * B]
-            s["znw"] = b.raw((B,), torch.int32)
+            s["znw"] = counts[(2 + k) * B:(3 + k) * B]
             s["ynw"] = ynw_all[k * B:(k + 1) * B]
             st[which] = s
             zh = zcat.sub(0 if which == "r" else Nz, Nz)
@@ -543,7 +560,9 @@ class ELIC_united(nn.Module):
             p.keep.append(t)
         self._dup(b, zcat.sub(0, Nz), zcat.sub(2 * Nz, Nz))
         ctx, ctx_rgb = self._ctx_buffers(b, B, h, w)
+        b.stage = "h_s"
         self._h_s(b, zcat, ctx.sub(0, 2 * M), ctx.sub(2 * M, 2 * M), None if ctx_rgb is None else ctx_rgb.sub(0, 2 * M))
+        b.stage = "chain"
         yhat = {"r": b.alloc(B, h, w, M, zero=True), "d": b.alloc(B, h, w, M, zero=True)}
         for which in ("r", "d"):
             t = yhat[which].buf
@@ -553,12 +572,15 @@ class ELIC_united(nn.Module):
 
         def code_step(which, idx, parity, params, g, coff):
             s = st[which]
+            b.stage = "coder"
             b.op("rgbd_ckbd_quantize_index", ys[which].ptr(), ys[which].cstride, ys[which].coff + coff,
                  params.ptr(), table[which].data_ptr(), table[which].numel(), bound[which], B, h, w, g, parity,
                  s["ysym"].data_ptr(), s["yidx"].data_ptr(), ny, offs[(idx, parity)],
                  yhat[which].ptr(), _DT[yhat[which].dtype], yhat[which].cstride, coff)
+            b.stage = "chain"
 
         self._context_chain(b, ctx, ctx_rgb, yhat["r"], yhat["d"], code_step)
+        b.stage = "coder"
         gr, gd = self._gc("r"), self._gc("d")
         same_tables = all(torch.equal(getattr(gr, n), getattr(gd, n)) for n in ("_quantized_cdf", "_cdf_length", "_offset"))
         if same_tables:   # the usual case: both Gaussian conditionals use get_scale_table()
@@ -573,12 +595,18 @@ class ELIC_united(nn.Module):
                 b.op("rgbd_rans_encode", s["ysym"].data_ptr(), s["yidx"].data_ptr(), ny, ny, B, ctypes.byref(t.struct),
                      s["yout"].data_ptr(), s["ycap"], s["ynw"].data_ptr())
                 p.keep.append(t)
-        p.io.update(st=st, shape=(hz, wz), y=ys, z=zs, yhat=yhat, ny=ny, nz=nz)
+        # all stream tails packed into one pinned host buffer by one kernel: [4B counts | words ...]; sized for
+        # 8 bits per symbol on average (a longer job falls back to per-stream copies in _collect_strings)
+        gcap = 2 * B * (ny + nz) // 4 + 64
+        p.io.update(st=st, shape=(hz, wz), y=ys, z=zs, yhat=yhat, ny=ny, nz=nz, counts=counts, gather_cap=gcap,
+                    gather_args=(yout_all.data_ptr(), ycap, 2 * B, zout_all.data_ptr(), zcap, 2 * B,
+                                 counts.data_ptr()))
         return p
 
     def _build_decoder(self, B, hz, wz):
         b = Builder(self.device, self.act_dtype, self.tensor_cores and self.precision == "bf16")
         p = b.prog
+        b.stage = "coder"
         Nz, M = self.N, self.M
         h, w = hz * 4, wz * 4
         H, W = h * 16, w * 16
@@ -591,7 +619,7 @@ class ELIC_united(nn.Module):
         word_off = b.raw((4 * B,), torch.int64)
         word_len = b.raw((4 * B,), torch.int64)
         state = b.raw((4 * B, 2), torch.int64)
-        p.io.update(words=words, word_off=word_off, word_len=word_len, words_cap=words_cap)
+        p.io.update(words=words, word_off=word_off, word_len=word_len, words_cap=words_cap, state=state)
         b.op("rgbd_rans_decode_init", words.data_ptr(), word_off.data_ptr(), 4 * B, state.data_ptr())
         st = {}
         for k, which in enumerate(("r", "d")):
@@ -613,7 +641,9 @@ class ELIC_united(nn.Module):
                  _DT[zh.dtype], zh.cstride, zh.coff)
         self._dup(b, zcat.sub(0, Nz), zcat.sub(2 * Nz, Nz))
         ctx, ctx_rgb = self._ctx_buffers(b, B, h, w)
+        b.stage = "h_s"
         self._h_s(b, zcat, ctx.sub(0, 2 * M), ctx.sub(2 * M, 2 * M), None if ctx_rgb is None else ctx_rgb.sub(0, 2 * M))
+        b.stage = "chain"
         yhat = {"r": b.alloc(B, h, w, M, zero=True), "d": b.alloc(B, h, w, M, zero=True)}
         for which in ("r", "d"):
             t = yhat[which].buf
@@ -626,6 +656,7 @@ class ELIC_united(nn.Module):
             n = g * h * (w // 2)
             off = offs[(idx, parity)]
             t = self._tables("gc", which)
+            b.stage = "coder"
             b.op("rgbd_ckbd_index", params.ptr(), table[which].data_ptr(), table[which].numel(), bound[which],
                  B, h, w, g, parity, s["yidx"].data_ptr(), ny, off)
             b.op("rgbd_rans_decode_chunk", words.data_ptr(), word_off[s["yslot"]:].data_ptr(),
@@ -634,10 +665,13 @@ class ELIC_united(nn.Module):
             b.op("rgbd_ckbd_dequant_scatter", s["ysym"].data_ptr(), ny, off, params.ptr(), B, h, w, g, parity,
                  yhat[which].ptr(), _DT[yhat[which].dtype], yhat[which].cstride, coff)
             p.keep.append(t)
+            b.stage = "chain"
 
         self._context_chain(b, ctx, ctx_rgb, yhat["r"], yhat["d"], code_step)
+        b.stage = "g_s"
         x_r, x_d = self._transform(b, self.g_s.rgb_synthesis_transform, self.g_s.depth_synthesis_transform,
                                    yhat["r"], yhat["d"])
+        b.stage = "io"
         out_r = b.raw((B, 3, H, W), torch.float32)
         out_d = b.raw((B, 1, H, W), torch.float32)
         b.op("rgbd_nhwc_to_nchw", x_r.ptr(), _DT[x_r.dtype], out_r.data_ptr(), B, 3, H, W, x_r.cstride, x_r.coff, 1)
@@ -668,7 +702,9 @@ class ELIC_united(nn.Module):
                  eb.likelihood_bound, zh.ptr(), _DT[zh.dtype], zh.cstride, zh.coff, lz.data_ptr())
         self._dup(b, zcat.sub(0, Nz), zcat.sub(2 * Nz, Nz))
         ctx, ctx_rgb = self._ctx_buffers(b, B, h, w)
+        b.stage = "h_s"
         self._h_s(b, zcat, ctx.sub(0, 2 * M), ctx.sub(2 * M, 2 * M), None if ctx_rgb is None else ctx_rgb.sub(0, 2 * M))
+        b.stage = "chain"
         yhat = {"r": b.alloc(B, h, w, M, zero=True), "d": b.alloc(B, h, w, M, zero=True)}
         for which in ("r", "d"):
             t = yhat[which].buf
@@ -682,8 +718,10 @@ class ELIC_united(nn.Module):
                  _DT[yhat[which].dtype], yhat[which].cstride, coff, lik[which][0].data_ptr(), M, coff)
 
         self._context_chain(b, ctx, ctx_rgb, yhat["r"], yhat["d"], code_step)
+        b.stage = "g_s"
         x_r, x_d = self._transform(b, self.g_s.rgb_synthesis_transform, self.g_s.depth_synthesis_transform,
                                    yhat["r"], yhat["d"])
+        b.stage = "io"
         out_r = b.raw((B, 3, H, W), torch.float32)
         out_d = b.raw((B, 1, H, W), torch.float32)
         b.op("rgbd_nhwc_to_nchw", x_r.ptr(), _DT[x_r.dtype], out_r.data_ptr(), B, 3, H, W, x_r.cstride, x_r.coff, 0)
@@ -719,6 +757,10 @@ class ELIC_united(nn.Module):
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
     def forward(self, rgb, depth):
+        if self.quant != "ste":
+            # codeOnePart (models/elic_united.py:99-103) quantises without the means for any other setting
+            raise NotImplementedError(f"forward() implements quant='ste' only (got {self.quant!r}); "
+                                      "compress()/decompress() do not depend on it")
         self._check_inputs(rgb, depth)
         B, _, H, W = rgb.shape
         p = self._program("forward", B, H, W)
@@ -747,17 +789,32 @@ class ELIC_united(nn.Module):
         B, _, H, W = rgb.shape
         p = self._program("encoder", B, H, W, slot=slot)
         stream = self._slot_stream(slot)
+        self._order_after_producer(stream, rgb, depth)
         with torch.cuda.device(self.device), torch.cuda.stream(stream):
             p.io["rgb"].copy_(rgb, non_blocking=True)
             p.io["depth"].copy_(depth, non_blocking=True)
             p.run(self.use_cuda_graph)
-            st = p.io["st"]
-            counts = torch.stack([st["r"]["ynw"], st["r"]["znw"], st["d"]["ynw"], st["d"]["znw"]])
-            counts_host = p.io.setdefault("counts_host", torch.empty((4, B), dtype=torch.int32).pin_memory())
-            counts_host.copy_(counts, non_blocking=True)
+            if "gather_host" not in p.io:
+                p.io["gather_host"] = torch.empty((4 * B + p.io["gather_cap"],), dtype=torch.int32, device="cpu",
+                                                  pin_memory=True)
+            gh = p.io["gather_host"]
+            # one kernel packs the counts and every stream's tail straight into pinned host memory (zero-copy
+            # stores over PCIe): the strings are complete on the host when `done` fires, no second D2H round trip
+            L.call("rgbd_gather_streams", *p.io["gather_args"], gh.data_ptr(), p.io["gather_cap"],
+                   ctypes.c_void_p(stream.cuda_stream))
             done = torch.cuda.Event()
             done.record(stream)
-        return _CompressHandle(self, p, B, stream, done, counts_host)
+        return _CompressHandle(self, p, B, stream, done, gh)
+
+    def _order_after_producer(self, stream, *tensors):
+        """A slot stream reads tensors the caller produced on ITS current stream: wait for that stream, and tell the
+        caching allocator the slot stream uses the storage (it must not be recycled while the copy is pending)."""
+        cur = torch.cuda.current_stream(self.device)
+        if stream != cur:
+            stream.wait_stream(cur)
+            for t in tensors:
+                if t.is_cuda:
+                    t.record_stream(stream)
 
     def _slot_stream(self, slot):
         if slot == 0:
@@ -767,24 +824,27 @@ class ELIC_united(nn.Module):
             streams[slot] = torch.cuda.Stream(self.device)
         return streams[slot]
 
-    def _collect_strings(self, p, B, counts):
-        """One packed D2H for all stream tails (the word counts are already on the host)."""
+    def _collect_strings(self, p, B, gh):
+        """Cut the packed host buffer [4B counts | words] (rgbd_gather_streams) into the per-stream strings."""
         st = p.io["st"]
+        host = gh.numpy()
+        counts = host[:4 * B].copy()
         if (counts < 0).any():
             raise L.RgbdError("rANS output buffer overflow (stream longer than 48 bits/symbol)")
-        pieces, meta = [], []
-        for row, (which, kind) in enumerate((("r", "y"), ("r", "z"), ("d", "y"), ("d", "z"))):
-            out, cap = st[which][kind + "out"], st[which][kind + "cap"]
-            for i in range(B):
-                n = int(counts[row, i])
-                pieces.append(out[i, cap - n:])
-                meta.append((which + kind, n))
-        host = torch.cat(pieces).cpu().numpy()
         res = {"ry": [], "rz": [], "dy": [], "dz": []}
-        pos = 0
-        for key, n in meta:
-            res[key].append(host[pos:pos + n].tobytes())
-            pos += n
+        order = [(k, i) for k in ("ry", "dy", "rz", "dz") for i in range(B)]
+        if int(counts.sum()) <= p.io["gather_cap"]:
+            words = host[4 * B:]
+            pos = 0
+            for (key, _), n in zip(order, counts):
+                res[key].append(words[pos:pos + n].tobytes())
+                pos += int(n)
+            return res
+        # rare: more than 8 bits per symbol on average — the packed buffer was too small, fetch stream by stream
+        for (key, i), n in zip(order, counts):
+            s_ = st[key[0]]
+            out, cap = s_[key[1] + "out"], s_[key[1] + "cap"]
+            res[key].append(out[i, cap - int(n):].cpu().numpy().tobytes())
         return res
 
     @torch.no_grad()
@@ -807,6 +867,8 @@ class ELIC_united(nn.Module):
         if len(ry) != B or len(dy) != B or len(dz) != B:
             raise ValueError(f"expected {B} y strings per modality (one per image), got {len(ry)} / {len(dy)}")
         hz, wz = int(shape[0]), int(shape[1])
+        if not (2 <= hz <= 1024 and 2 <= wz <= 1024):
+            raise ValueError(f"latent shape {(hz, wz)} out of range (images of 128 .. 65536 pixels per side)")
         p = self._program("decoder", B, hz, wz, slot=slot)
         streams = rz + dz + ry + dy
         lens = np.array([len(s) // 4 for s in streams], dtype=np.int64)
@@ -818,8 +880,8 @@ class ELIC_united(nn.Module):
         if total > p.io["words_cap"]:
             raise ValueError("streams larger than the decoder's word buffer")
         if "words_host" not in p.io:   # pinned staging so the H2D copies are asynchronous
-            p.io["words_host"] = torch.empty(p.io["words_cap"], dtype=torch.int32).pin_memory()
-            p.io["meta_host"] = torch.empty((2, 4 * B), dtype=torch.int64).pin_memory()
+            p.io["words_host"] = torch.empty(p.io["words_cap"], dtype=torch.int32, device="cpu", pin_memory=True)
+            p.io["meta_host"] = torch.empty((2, 4 * B), dtype=torch.int64, device="cpu", pin_memory=True)
         stream = self._slot_stream(slot)
         with torch.cuda.device(self.device), torch.cuda.stream(stream):
             prev = p.io.get("h2d_done")
@@ -840,30 +902,39 @@ class ELIC_united(nn.Module):
             ev.record(stream)
             p.io["h2d_done"] = ev
             p.run(self.use_cuda_graph)
+            if "state_host" not in p.io:
+                p.io["state_host"] = torch.empty((4 * B, 2), dtype=torch.int64, device="cpu", pin_memory=True)
+            p.io["state_host"].copy_(p.io["state"], non_blocking=True)
             done = torch.cuda.Event()
             done.record(stream)
-        return _DecompressHandle(p, stream, done)
+        return _DecompressHandle(p, stream, done, lens)
 
 
 class _CompressHandle:
-    def __init__(self, net, prog, B, stream, done, counts_host):
-        self.net, self.prog, self.B, self.stream, self.done, self.counts_host = net, prog, B, stream, done, counts_host
+    def __init__(self, net, prog, B, stream, done, gather_host):
+        self.net, self.prog, self.B, self.stream, self.done, self.gather_host = net, prog, B, stream, done, gather_host
 
     def result(self):
         self.done.synchronize()
         p = self.prog
         with torch.cuda.device(self.net.device), torch.cuda.stream(self.stream):
-            strings = self.net._collect_strings(p, self.B, self.counts_host.numpy().copy())
+            strings = self.net._collect_strings(p, self.B, self.gather_host)
         return {"r_strings": [strings["ry"], strings["rz"]], "d_strings": [strings["dy"], strings["dz"]],
                 "shape": torch.Size(p.io["shape"])}
 
 
 class _DecompressHandle:
-    def __init__(self, prog, stream, done):
-        self.prog, self.stream, self.done = prog, stream, done
+    def __init__(self, prog, stream, done, word_lens):
+        self.prog, self.stream, self.done, self.word_lens = prog, stream, done, word_lens
 
     def result(self, clone=True):
         self.done.synchronize()
+        # a valid stream is consumed exactly: the decoder ends on its last word (reads past the end return zeros and
+        # would otherwise decode a truncated or foreign stream silently to garbage)
+        pos = self.prog.io["state_host"].numpy()[:, 1]
+        if (pos != self.word_lens).any():
+            bad = int(np.nonzero(pos != self.word_lens)[0][0])
+            raise ValueError(f"corrupt stream {bad}: decoder stopped at word {int(pos[bad])} of {int(self.word_lens[bad])}")
         r, d = self.prog.io["out_r"], self.prog.io["out_d"]
         if clone:
             with torch.cuda.stream(self.stream):

@@ -229,6 +229,7 @@ class Builder:
         self._wscratch = None   # per-image SE-folded filters of the layer being run (shared by all layers)
         self._sched = None      # tile counters of the persistent conv kernels (one int32 per plan, zero between launches)
         self._sched_used = 0
+        self.stage = ""         # label of the part of the codec being compiled (g_a, h_a, h_s, chain, coder, g_s, io)
         # tcgen05 path: bf16 activations only
         self.tensor_cores = (act_dtype == torch.bfloat16) if tensor_cores is None else tensor_cores
 
@@ -242,7 +243,7 @@ class Builder:
         # 16-byte aligned pixel rows (TMA global strides, vector epilogue stores)
         Cp = (Cc + 7) // 8 * 8 if dtype == torch.bfloat16 else Cc
         shape = (N, H, W, Cp)
-        esz = torch.empty((), dtype=dtype).element_size()
+        esz = 2 if dtype == torch.bfloat16 else 4
         nbytes = N * H * W * Cp * esz
         need = (nbytes + 1023) // 1024 * 1024          # 1 KB granules keep every carve aligned
         chunks = self.prog.pool.setdefault("chunks", [])   # [tensor, free ranges [(off, size)] sorted by off]
@@ -311,6 +312,7 @@ class Builder:
             if rc:
                 L.check(rc, name)
         run.label = label
+        run.stage = self.stage
         self.prog.ops.append(run)
         return run
 

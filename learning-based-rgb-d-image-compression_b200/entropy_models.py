@@ -6,9 +6,12 @@ rANS) is done by the CUDA kernels behind the C-ABI.
 
 Reference: CompressAI/compressai/entropy_models/entropy_models.py
   EntropyModel buffers :88-91, EntropyBottleneck :269-446, GaussianConditional :450-568.
-Table construction runs on the CPU in fp32 exactly as the reference harness does
-(testing/tester.py:100-108 calls update() before .to("cuda")), and goes through
-rgbd_pmf_to_quantized_cdf (C-ABI, host) instead of compressai._CXX.
+Table construction always runs on the CPU in fp32, whatever the default tensor type is: the
+reference harness sets torch.set_default_tensor_type('torch.cuda.FloatTensor') (playground/test.py:20),
+so every factory call here names its device.  (The reference computes the tables on whatever
+device the buffers happen to live on; the CPU is the one choice that gives the same tables on
+every machine, and it is what the golden vectors were generated with.)  The pmf -> cdf step goes
+through rgbd_pmf_to_quantized_cdf (C-ABI, host) instead of compressai._CXX.
 """
 import ctypes as C
 import math
@@ -118,7 +121,7 @@ class EntropyModelBase(nn.Module):
         return self._cdf_length
 
     def _pmf_to_cdf(self, pmf, tail_mass, pmf_length, max_length):
-        cdf = torch.zeros((len(pmf_length), max_length + 2), dtype=torch.int32)
+        cdf = torch.zeros((len(pmf_length), max_length + 2), dtype=torch.int32, device="cpu")
         for i in range(len(pmf_length)):
             prob = torch.cat((pmf[i, : int(pmf_length[i])], tail_mass[i]), dim=0)
             q = pmf_to_quantized_cdf(prob, 16)
@@ -184,7 +187,7 @@ class EntropyBottleneck(EntropyModelBase):
         pmf_start = medians - minima
         pmf_length = maxima + minima + 1
         max_length = int(pmf_length.max())
-        samples = torch.arange(max_length)[None, :] + pmf_start[:, None, None]
+        samples = torch.arange(max_length, device="cpu")[None, :] + pmf_start[:, None, None]
         lower = self._logits_cumulative(samples - 0.5)
         upper = self._logits_cumulative(samples + 0.5)
         sign = -torch.sign(lower + upper)
@@ -216,8 +219,10 @@ class EntropyBottleneck(EntropyModelBase):
 
 
 def get_scale_table(lo=0.11, hi=256, levels=64):
-    """utils/moduleFunc.py:11-12"""
-    return torch.exp(torch.linspace(math.log(lo), math.log(hi), levels))
+    """utils/moduleFunc.py:11-12, always evaluated on the CPU: the table (and with it every CDF) must not depend on
+    which device happens to be the default (the reference harness makes CUDA the default; exp differs in the
+    last ulp between devices)."""
+    return torch.exp(torch.linspace(math.log(lo), math.log(hi), levels, device="cpu"))
 
 
 class GaussianConditional(EntropyModelBase):
@@ -234,7 +239,11 @@ class GaussianConditional(EntropyModelBase):
         if self._offset.numel() > 0 and not force:
             return False
         dev = self.scale_table.device
-        self.scale_table = torch.Tensor(tuple(float(s) for s in scale_table)).to(dev)
+        if isinstance(scale_table, torch.Tensor):
+            vals = scale_table.detach().to(device="cpu", dtype=torch.float32).reshape(-1)
+        else:
+            vals = torch.tensor([float(v) for v in scale_table], dtype=torch.float32, device="cpu")
+        self.scale_table = vals.clone().to(dev)
         self.update()
         return True
 
@@ -250,7 +259,7 @@ class GaussianConditional(EntropyModelBase):
         pmf_center = torch.ceil(table * multiplier).int()
         pmf_length = 2 * pmf_center + 1
         max_length = int(torch.max(pmf_length))
-        samples = torch.abs(torch.arange(max_length).int() - pmf_center[:, None]).float()
+        samples = torch.abs(torch.arange(max_length, device="cpu").int() - pmf_center[:, None]).float()
         scale = table.unsqueeze(1)
         upper = self._std_cumulative((0.5 - samples) / scale)
         lower = self._std_cumulative((-0.5 - samples) / scale)

@@ -76,6 +76,7 @@ _PROTOS = {
     "rgbd_eb_dequantize": [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp],
     "rgbd_eb_likelihood": [_vp, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _i32, _i32, _i32, _vp, _vp],
     "rgbd_rans_encode": [_vp, _vp, _i64, _i32, _i32, C.POINTER(RansTables), _vp, _i64, _vp, _vp],
+    "rgbd_gather_streams": [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _vp],
     "rgbd_rans_decode_init": [_vp, _vp, _i32, _vp, _vp],
     "rgbd_rans_decode_chunk": [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i32, C.POINTER(RansTables), _vp],
     "rgbd_pmf_to_quantized_cdf": [_vp, _i32, _i32, _vp],

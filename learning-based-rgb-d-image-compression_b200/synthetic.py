@@ -27,7 +27,7 @@ PRESETS = {
 
 def _gen(key, seed):
     h = hashlib.sha256(f"{seed}:{key}".encode()).digest()
-    g = torch.Generator()
+    g = torch.Generator(device="cpu")
     g.manual_seed(int.from_bytes(h[:7], "little"))
     return g
 
@@ -47,14 +47,14 @@ def synthetic_state_dict(model, seed=0, preset="mid"):
                 widths = (1, 3, 3, 3, 3, 1)
                 i = int(leaf[-1])
                 scale = 10 ** (1 / 5)
-                v = torch.full(shape, math.log(math.expm1(1 / scale / widths[i + 1])))
+                v = torch.full(shape, math.log(math.expm1(1 / scale / widths[i + 1])), device="cpu")
             elif leaf.startswith("_bias"):
-                v = torch.rand(shape, generator=g) - 0.5
+                v = torch.rand(shape, generator=g, device="cpu") - 0.5
             elif leaf.startswith("_factor"):
-                v = torch.zeros(shape)
+                v = torch.zeros(shape, device="cpu")
             elif leaf == "quantiles":
-                v = torch.tensor([-10.0, 0.0, 10.0]).repeat(shape[0], 1, 1)
-                v[:, 0, 1] = (torch.rand(shape[0], generator=g) - 0.5) * 2.0   # non-trivial medians
+                v = torch.tensor([-10.0, 0.0, 10.0], device="cpu").repeat(shape[0], 1, 1)
+                v[:, 0, 1] = (torch.rand(shape[0], generator=g, device="cpu") - 0.5) * 2.0   # non-trivial medians
                 v[:, 0, 0] += v[:, 0, 1]
                 v[:, 0, 2] += v[:, 0, 1]
             else:
@@ -69,13 +69,13 @@ def synthetic_state_dict(model, seed=0, preset="mid"):
                 k = shape[2]
                 fan_in = shape[0] * (k * k / 4.0 if k == 5 else k * k)
             std = math.sqrt(2.0 / fan_in)
-            v = torch.randn(shape, generator=g) * std
+            v = torch.randn(shape, generator=g, device="cpu") * std
             if ".branch.4." in key or ".conv.4." in key:
                 v = v * 0.5     # residual branches: keep the sum's variance from growing too fast
         elif leaf == "weight" and len(shape) == 2:
-            v = torch.randn(shape, generator=g) * math.sqrt(1.0 / shape[1])
+            v = torch.randn(shape, generator=g, device="cpu") * math.sqrt(1.0 / shape[1])
         elif leaf == "bias":
-            v = (torch.rand(shape, generator=g) - 0.5) * 0.1
+            v = (torch.rand(shape, generator=g, device="cpu") - 0.5) * 0.1
         else:
             v = t.clone()
         out[key] = v.to(t.dtype)
@@ -88,7 +88,7 @@ def synthetic_state_dict(model, seed=0, preset="mid"):
         if "entropy_parameters" in key and key.endswith("fusion.4.bias"):
             g = _gen(key + ":scale", seed)
             n = out[key].shape[0] // 2
-            out[key][:n] = torch.exp(torch.rand(n, generator=g) * (math.log(hi) - math.log(lo)) + math.log(lo))
+            out[key][:n] = torch.exp(torch.rand(n, generator=g, device="cpu") * (math.log(hi) - math.log(lo)) + math.log(lo))
             out[key][n:] *= 0.0
         if "entropy_parameters" in key and key.endswith("fusion.4.weight"):
             out[key] = out[key] * 0.25   # predicted scales/means stay near their bias
@@ -110,16 +110,16 @@ def synthetic_pairs(n, height=480, width=640, seed=1234, depth_div=10000.0):
     low-pass filtered noise so the statistics are image-like. Returns fp32 NCHW on the CPU."""
     rgbs, depths = [], []
     for i in range(n):
-        g = torch.Generator()
+        g = torch.Generator(device="cpu")
         g.manual_seed(seed + i)
-        noise = torch.rand(1, 3, height + 8, width + 8, generator=g)
+        noise = torch.rand(1, 3, height + 8, width + 8, generator=g, device="cpu")
         smooth = torch.nn.functional.avg_pool2d(noise, 9, stride=1)
         smooth = (smooth - smooth.amin()) / (smooth.amax() - smooth.amin())
-        detail = torch.rand(1, 3, height, width, generator=g) * 0.08
+        detail = torch.rand(1, 3, height, width, generator=g, device="cpu") * 0.08
         rgb = torch.round(((smooth * 0.92 + detail).clamp(0, 1)) * 255.0) / 255.0
-        yy = torch.linspace(0, 1, height).view(1, 1, -1, 1)
-        xx = torch.linspace(0, 1, width).view(1, 1, 1, -1)
-        dn = torch.nn.functional.avg_pool2d(torch.rand(1, 1, height + 16, width + 16, generator=g), 17, stride=1)
+        yy = torch.linspace(0, 1, height, device="cpu").view(1, 1, -1, 1)
+        xx = torch.linspace(0, 1, width, device="cpu").view(1, 1, 1, -1)
+        dn = torch.nn.functional.avg_pool2d(torch.rand(1, 1, height + 16, width + 16, generator=g, device="cpu"), 17, stride=1)
         d16 = torch.round(700.0 + (9999.0 - 700.0) * (0.5 * yy + 0.2 * xx + 0.3 * (dn - dn.amin()) / (dn.amax() - dn.amin())))
         rgbs.append(rgb)
         depths.append(d16 / depth_div)

@@ -1,6 +1,6 @@
 """Per-op timing of one encoder + decoder program run (CUDA events per op)."""
 import sys, os, ctypes as C, collections, re
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, rgbd_b200
 from gpu_utils import make_model

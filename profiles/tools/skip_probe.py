@@ -3,7 +3,7 @@ holds plausible data) = what the conv pipeline alone sustains; the difference to
 serial chains / SM fencing cost.
 Needs a library built with the probes: RGBD_BUILD_DEFINES=-DRGBD_TIMING_PROBES python <pkg>/build.py --force"""
 import os, sys, ctypes as C
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, rgbd_b200
 from gpu_utils import make_model

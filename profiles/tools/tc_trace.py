@@ -1,6 +1,6 @@
 """Where does each warp role of conv_halo_kernel stall?  Cycle counters of CTA 0 for single layers."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, torch.nn as nn
 DEV = "cuda:0"

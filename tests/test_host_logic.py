@@ -160,10 +160,41 @@ def test_load_state_dict_resizes_tables():
     b.load_state_dict(a.state_dict())          # checkpoint saved after update() into a fresh model
     assert torch.equal(b.rgb_gaussian_conditional.quantized_cdf, a.rgb_gaussian_conditional.quantized_cdf)
     b.load_state_dict(a.state_dict())          # and into an already-updated one
+    bad = dict(a.state_dict())
+    bad.pop("g_a.rgb_analysis_transform.0.weight")
     with pytest.raises(RuntimeError):
-        bad = dict(a.state_dict())
-        bad.pop("g_a.rgb_analysis_transform.0.weight")
-        b.load_state_dict(bad)
+        b.load_state_dict(bad, strict=True)
+    # the reference's default (models/elic_united.py:588-620): strict is tried first, then a non-strict load
+    rv = b.load_state_dict(bad)
+    assert "g_a.rgb_analysis_transform.0.weight" in rv.missing_keys
+
+
+def test_update_does_not_depend_on_the_default_device():
+    """playground/test.py:20 makes CUDA the default tensor type: every factory call inside update() has to name its
+    device.  Emulated here with the `meta` default device (a device-less factory call would make a meta tensor
+    and the mix with the CPU tensors raises)."""
+    a = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4)
+    a.update(force=True)
+    want = {k: v.clone() for k, v in a.state_dict().items() if "_quantized_cdf" in k or "_offset" in k or "_cdf_length" in k}
+    b = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4)
+    b.load_state_dict({k: v for k, v in a.state_dict().items()})
+    torch.set_default_device("meta")
+    try:
+        b.update(force=True)
+        perm = b._ctx_layout(1)[1]["d_nonanchor"]
+    finally:
+        torch.set_default_device("cpu")
+    assert perm.device.type == "cpu"
+    for k, v in want.items():
+        assert torch.equal(b.state_dict()[k], v), k
+
+
+def test_forward_rejects_non_ste_quant():
+    cfg = rgbd_b200.model_config()
+    cfg["quant"] = "noise"
+    net = rgbd_b200.ELIC_united(config=cfg, channel=4)
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 3, 128, 128), torch.zeros(1, 1, 128, 128))
 
 
 def test_exact_reciprocal_division():
@@ -215,3 +246,31 @@ def test_plan_arena_reuses_and_coalesces_storage():
     assert e.ptr() == pa and e.cstride == 24 and b.prog.bytes == 64 << 20
     z = b.alloc(1, 8, 8, 16, zero=True)           # zero-initialised buffers get a private, exact chunk
     assert len(b.prog.pool["chunks"]) == 2 and float(z.buf.float().abs().sum()) == 0.0
+
+
+def test_oracle_tables_equal_product_update(built_lib):
+    """oracle/tables.py (the CPU arm's update(force=True), built on oracle/_ref/_CXX or the C restatement) produces the
+    tables the product's update() produces."""
+    from oracle.tables import updated_state_dict
+    net = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4)
+    sd0 = rgbd_b200.synthetic.synthetic_state_dict(net, 0, "mid")
+    net.load_state_dict(sd0)
+    net.update(force=True)
+    want = net.state_dict()
+    got = updated_state_dict(sd0)
+    assert list(got) == list(want)
+    for k in want:
+        assert got[k].shape == want[k].shape and torch.equal(got[k], want[k]), k
+
+
+def test_cpu_arm_does_not_load_the_product_library():
+    """bench.py --impl reference / cpu_baseline must time the oracle only (the arm used to map librgbd_b200.so)."""
+    import subprocess
+    import sys
+    code = ("import sys, types; sys.argv=['bench.py','--height','128','--width','128','--preset','mid'];"
+            "import bench; a=bench.parse(); r=bench.cpu_arm(a,1,1,0);"
+            "maps=open('/proc/self/maps').read(); print('LOADED' if 'librgbd_b200' in maps else 'CLEAN', r['value']>0)")
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().splitlines()[-1] == "CLEAN True", out.stdout
