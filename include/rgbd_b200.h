@@ -120,6 +120,32 @@ int rgbd_conv_tc_plan_create(const rgbd_conv_desc *d, int32_t cin_pad, rgbd_conv
 int rgbd_conv_tc_run(const rgbd_conv_tc_plan *p, void *stream);
 void rgbd_conv_tc_plan_destroy(rgbd_conv_tc_plan *p);
 
+/* Fused bottleneck block on the tensor cores (bf16 NHWC in / out):
+ *     y = act( res + W3 * relu( W2 (*) relu( W1 * x + b1 ) + b2 ) + b3 ),   1x1 (Cin -> 96), 3x3 (96 -> 96, pad 1), 1x1 (96 -> Cout)
+ * = ResidualBottleneck (modules/layers/res_blk.py:7-27; res = x, or the output of its 1x1 skip conv) and
+ * AttentionBlock.ResidualUnit (CompressAI/compressai/layers/layers.py:178-197; res = x, final_relu = 1) in ONE launch,
+ * with both 96-channel intermediates kept in shared memory / TMEM.  Weights are bf16, K-major:
+ *   w1 [96][Cin], w3 [Cout][128] (K padded 96 -> 128 with zeros),
+ *   w2 [14 planes][96][64]: plane t < 9 = tap t (ky * 3 + kx), input channels 0-63; plane 9 + i = input channels 64-95 of
+ *   tap 2 i in elements [0, 32) and of tap 2 i + 1 in elements [32, 64) of each row (zeros for the missing tap 9).
+ * Cin % 64 == 0, Cmid == 96, Cout == 192; every view 16-byte aligned. */
+typedef struct rgbd_rb_desc {
+    const void *x, *res;
+    void *y;
+    const void *w1, *w2, *w3;
+    const float *b1, *b2, *b3;     /* [96], [96], [Cout] or NULL */
+    int32_t N, H, W;
+    int32_t Cin, x_cstride, x_coff;
+    int32_t Cmid, Cout;
+    int32_t res_cstride, res_coff, y_cstride, y_coff;
+    int32_t final_relu;
+    int32_t _pad;
+} rgbd_rb_desc;
+typedef struct rgbd_rb_plan rgbd_rb_plan;
+int rgbd_rb_plan_create(const rgbd_rb_desc *d, rgbd_rb_plan **out);
+int rgbd_rb_run(const rgbd_rb_plan *p, void *stream);
+void rgbd_rb_plan_destroy(rgbd_rb_plan *p);
+
 /* ------------------------------------------------------------------------------------------
  * Small spatial / channel ops of the transforms.
  * ------------------------------------------------------------------------------------------ */
@@ -269,6 +295,20 @@ int rgbd_rans_decode_chunk(const uint32_t *words, const int64_t *word_off, const
                            int32_t n_streams, rgbd_rans_dec_state *state, const uint8_t *idx,
                            int32_t *sym, int64_t stream_stride, int64_t chunk_off, int32_t n_sym,
                            const rgbd_rans_tables *t, void *stream);
+
+/* Multi-stream layout (opt-in: the reference decoder reads one y stream): the y symbols of an image are cut
+ * into equal sub-streams of n_sym symbols (a whole number of channels of one checkerboard half), each of them a complete
+ * RansEncoder.encode_with_indexes string of its own (rgbd_rans_encode with stream_stride = n_sym).  One coding step of
+ * the decoder then decodes `per_group` whole sub-streams of each of the n_groups images concurrently — one warp each,
+ * fresh state from the stream's first two words (RansDecoder.set_stream + decode_stream, rans_interface.cpp:278-351):
+ *   stream (g, m), m < per_group: symbols / indexes at g * group_stride + m * stream_stride + chunk_off,
+ *   its words described by word_off / word_len [g * slot_group_stride + slot_base + m]; the final decoder state goes to
+ *   state[same slot] (pos == word_len there means the stream was consumed exactly). */
+int rgbd_rans_decode_streams(const uint32_t *words, const int64_t *word_off, const int64_t *word_len,
+                             int32_t n_groups, int32_t per_group, int32_t slot_base, int32_t slot_group_stride,
+                             rgbd_rans_dec_state *state, const uint8_t *idx, int32_t *sym, int64_t group_stride,
+                             int64_t stream_stride, int64_t chunk_off, int32_t n_sym, const rgbd_rans_tables *t,
+                             void *stream);
 
 /* pmf_to_quantized_cdf (ops.cpp:24-81). Host function. cdf has n+1 entries. */
 int rgbd_pmf_to_quantized_cdf(const float *pmf, int32_t n, int32_t precision, uint32_t *cdf);

@@ -289,12 +289,23 @@ __device__ __forceinline__ int32_t dec_escape(DecState &d, WordFeed &feed, int l
     return value;
 }
 
+// Which streams a decode launch works on.  Stream s of the launch = (group s / per_group, member s % per_group):
+//   symbols / indexes at group * group_stride + member * stream_stride + chunk_off,
+//   word table slot (word_off / word_len / state index) = group * slot_group_stride + slot_base + member.
+// The resumable single-stream layout is one group (per_group = n_streams, slot_base = 0); the multi-stream layout
+// decodes, per coding step, `per_group` whole sub-streams of every image (fresh = 1: the state starts from the
+// stream's first two words instead of state[]).
+struct DecodeMap {
+    int32_t per_group, slot_base, slot_group_stride, fresh;
+    int64_t group_stride;
+};
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 rans_decode_kernel(const uint32_t *__restrict__ words, const int64_t *__restrict__ word_off,
                    const int64_t *__restrict__ word_len, int32_t n_streams,
                    rgbd_rans_dec_state *__restrict__ state, const uint8_t *__restrict__ idx,
                    int32_t *__restrict__ sym, int64_t stream_stride, int64_t chunk_off,
-                   int32_t n_sym, rgbd_rans_tables t) {
+                   int32_t n_sym, rgbd_rans_tables t, DecodeMap map) {
     extern __shared__ __align__(16) uint16_t s_cdf[];
     __shared__ TableSmem meta;
     __shared__ int4 s_meta[kWarpsPerBlock][32];   // (base, length, offset, -) of the batch's tables
@@ -306,16 +317,25 @@ rans_decode_kernel(const uint32_t *__restrict__ words, const int64_t *__restrict
     const int wib = threadIdx.x >> 5;
     const int s = blockIdx.x * kWarpsPerBlock + wib;
     if (s >= n_streams) return;
+    const int grp = s / map.per_group, mem = s - grp * map.per_group;
+    const int slot = grp * map.slot_group_stride + map.slot_base + mem;
+    const int64_t sym_off = (int64_t)grp * map.group_stride + (int64_t)mem * stream_stride + chunk_off;
 
     DecState d;
-    d.x = state[s].x;
-    d.pos = state[s].pos;
+    const uint32_t *my_words = words + word_off[slot];
+    if (map.fresh) {   // Rans64DecInit (rans64.h:107-115)
+        d.x = (uint64_t)my_words[0] | ((uint64_t)my_words[1] << 32);
+        d.pos = 2;
+    } else {
+        d.x = state[slot].x;
+        d.pos = state[slot].pos;
+    }
     WordFeed feed;
-    feed.init(words + word_off[s], word_len[s], d.pos, lane);
+    feed.init(my_words, word_len[slot], d.pos, lane);
     d.wnext = feed.take(d.pos, lane);
 
-    const uint8_t *my_idx = idx + (int64_t)s * stream_stride + chunk_off;
-    int32_t *my_sym = sym + (int64_t)s * stream_stride + chunk_off;
+    const uint8_t *my_idx = idx + sym_off;
+    int32_t *my_sym = sym + sym_off;
     int4 *mrow = s_meta[wib];
     const uint32_t cdf_sa = (uint32_t)__cvta_generic_to_shared(s_cdf);
     const uint32_t lane2 = (uint32_t)lane * 2u;
@@ -396,8 +416,8 @@ rans_decode_kernel(const uint32_t *__restrict__ words, const int64_t *__restrict
         if (i < n_sym) my_sym[i] = my_out;
     }
     if (lane == 0) {
-        state[s].x = d.x;
-        state[s].pos = d.pos;
+        state[slot].x = d.x;
+        state[slot].pos = d.pos;
     }
 }
 
@@ -493,17 +513,14 @@ extern "C" int rgbd_rans_decode_init(const uint32_t *words, const int64_t *word_
     return RGBD_OK;
 }
 
-extern "C" int rgbd_rans_decode_chunk(const uint32_t *words, const int64_t *word_off,
-                                      const int64_t *word_len, int32_t n_streams,
-                                      rgbd_rans_dec_state *state, const uint8_t *idx, int32_t *sym,
-                                      int64_t stream_stride, int64_t chunk_off, int32_t n_sym,
-                                      const rgbd_rans_tables *t, void *stream) {
-    RGBD_CHECK_ARG(words && word_off && word_len && state && idx && sym && t, "null pointer");
-    RGBD_CHECK_ARG(n_sym >= 0 && n_streams >= 0, "sizes");
-    RGBD_CHECK_ARG(t->n_tables > 0 && t->n_tables <= kMaxTables, "n_tables must be in 1..256");
+static int launch_decode(const uint32_t *words, const int64_t *word_off, const int64_t *word_len, int32_t n_streams,
+                         rgbd_rans_dec_state *state, const uint8_t *idx, int32_t *sym, int64_t stream_stride,
+                         int64_t chunk_off, int32_t n_sym, const rgbd_rans_tables *t, const DecodeMap &map, void *stream) {
     const size_t smem = cdf_smem_bytes(t);
-    RGBD_CHECK_ARG(smem <= 200 * 1024, "CDF tables do not fit in shared memory");
-    if (n_streams == 0 || n_sym == 0) return RGBD_OK;
+    if (smem > 200 * 1024) {
+        rgbd_set_error("rans decode: CDF tables do not fit in shared memory");
+        return RGBD_E_INVALID;
+    }
 #ifdef RGBD_TIMING_PROBES
     if (getenv("RGBD_RANS_SKIP")) {
         if (atoi(getenv("RGBD_RANS_SKIP")) == 2) rans_sleep_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((long long)n_sym * 150);
@@ -524,9 +541,39 @@ extern "C" int rgbd_rans_decode_chunk(const uint32_t *words, const int64_t *word
     }
     const int grid = (n_streams + kWarpsPerBlock - 1) / kWarpsPerBlock;
     rans_decode_kernel<<<grid, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
-        words, word_off, word_len, n_streams, state, idx, sym, stream_stride, chunk_off, n_sym, *t);
+        words, word_off, word_len, n_streams, state, idx, sym, stream_stride, chunk_off, n_sym, *t, map);
     RGBD_LAUNCH_CHECK();
     return RGBD_OK;
+}
+
+extern "C" int rgbd_rans_decode_chunk(const uint32_t *words, const int64_t *word_off,
+                                      const int64_t *word_len, int32_t n_streams,
+                                      rgbd_rans_dec_state *state, const uint8_t *idx, int32_t *sym,
+                                      int64_t stream_stride, int64_t chunk_off, int32_t n_sym,
+                                      const rgbd_rans_tables *t, void *stream) {
+    RGBD_CHECK_ARG(words && word_off && word_len && state && idx && sym && t, "null pointer");
+    RGBD_CHECK_ARG(n_sym >= 0 && n_streams >= 0, "sizes");
+    RGBD_CHECK_ARG(t->n_tables > 0 && t->n_tables <= kMaxTables, "n_tables must be in 1..256");
+    if (n_streams == 0 || n_sym == 0) return RGBD_OK;
+    DecodeMap map;
+    map.per_group = n_streams; map.slot_base = 0; map.slot_group_stride = 0; map.fresh = 0; map.group_stride = 0;
+    return launch_decode(words, word_off, word_len, n_streams, state, idx, sym, stream_stride, chunk_off, n_sym, t, map, stream);
+}
+
+extern "C" int rgbd_rans_decode_streams(const uint32_t *words, const int64_t *word_off, const int64_t *word_len,
+                                        int32_t n_groups, int32_t per_group, int32_t slot_base, int32_t slot_group_stride,
+                                        rgbd_rans_dec_state *state, const uint8_t *idx, int32_t *sym, int64_t group_stride,
+                                        int64_t stream_stride, int64_t chunk_off, int32_t n_sym, const rgbd_rans_tables *t,
+                                        void *stream) {
+    RGBD_CHECK_ARG(words && word_off && word_len && state && idx && sym && t, "null pointer");
+    RGBD_CHECK_ARG(n_sym >= 0 && n_groups >= 0 && per_group >= 0 && slot_base >= 0 && slot_group_stride >= per_group, "sizes");
+    RGBD_CHECK_ARG(t->n_tables > 0 && t->n_tables <= kMaxTables, "n_tables must be in 1..256");
+    if (n_groups == 0 || per_group == 0 || n_sym == 0) return RGBD_OK;
+    DecodeMap map;
+    map.per_group = per_group; map.slot_base = slot_base; map.slot_group_stride = slot_group_stride; map.fresh = 1;
+    map.group_stride = group_stride;
+    return launch_decode(words, word_off, word_len, n_groups * per_group, state, idx, sym, stream_stride, chunk_off, n_sym, t, map,
+                         stream);
 }
 
 extern "C" int rgbd_gather_streams(const uint32_t *out_a, int64_t cap_a, int32_t n_a, const uint32_t *out_b,

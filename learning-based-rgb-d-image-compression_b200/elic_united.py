@@ -22,6 +22,7 @@ B per-image strings (the reference would interleave the batch into one stream, w
 harness never does: utils/IOutils.py:84-86, config/args.py:66-68).
 """
 import ctypes
+import os
 import time
 
 import numpy as np
@@ -89,6 +90,14 @@ class ELIC_united(nn.Module):
         self.precision = kwargs.get("precision", "fp32")   # "fp32" | "bf16"
         self.use_cuda_graph = kwargs.get("cuda_graph", False)
         self.tensor_cores = kwargs.get("tensor_cores", True)   # bf16 mode: tcgen05 convs (False: CUDA cores)
+        # bf16 tensor-core mode: ResidualBottleneck / ResidualUnit as ONE launch with on-chip intermediates
+        self.fuse_blocks = kwargs.get("fuse_blocks", os.environ.get("RGBD_FUSE_BLOCKS", "1") != "0")
+        # Bitstream layout of the y latents.  "single" (default) = the reference's: one rANS stream per image and modality
+        # (decodable by the reference).  "multi" (opt-in) = that stream cut into equal sub-streams of
+        # `sub_channels` channels of one checkerboard half, each a complete RansEncoder string, carried as further strings
+        # of the same container entry: every coding step then decodes many short streams concurrently.
+        self.stream_layout = kwargs.get("stream_layout", "single")
+        self.sub_channels = int(kwargs.get("sub_channels", 4))
         self._packed = None      # id(module) -> PackedConv, rebuilt when weights change
         self._programs = {}
         self._aux = {}
@@ -185,6 +194,14 @@ class ELIC_united(nn.Module):
     # ------------------------------------------------------------------ graph pieces
     def _rb(self, b, m, x, out=None):
         """ResidualBottleneck (res_blk.py:7-27): x (+skip) + 1x1(relu(3x3(relu(1x1 x))))"""
+        pcs = [self._pc(m.branch[i]) for i in (0, 2, 4)]
+        if self.fuse_blocks and b.can_fuse_block(*pcs, x):
+            # one launch, intermediates on chip (csrc/conv_rb.cu); the optional 1x1 skip conv stays a launch of its own
+            idn = x if m.skip is None else b.conv(self._pc(m.skip), x)
+            y = b.fused_block(*pcs, x, res=idn, out=out)
+            if idn is not x:
+                b.release(idn)
+            return y
         t1 = b.conv(self._pc(m.branch[0]), x, act=RELU)
         t2 = b.conv(self._pc(m.branch[2]), t1, act=RELU)
         b.release(t1)
@@ -198,6 +215,9 @@ class ELIC_united(nn.Module):
 
     def _ru(self, b, m, x):
         """AttentionBlock.ResidualUnit (layers.py:178-197): relu(x + conv(x))"""
+        pcs = [self._pc(m.conv[i]) for i in (0, 2, 4)]
+        if self.fuse_blocks and b.can_fuse_block(*pcs, x):
+            return b.fused_block(*pcs, x, res=x, final_relu=True)
         t1 = b.conv(self._pc(m.conv[0]), x, act=RELU)
         t2 = b.conv(self._pc(m.conv[2]), t1, act=RELU)
         b.release(t1)
@@ -490,6 +510,16 @@ class ELIC_united(nn.Module):
                 p += g * h * (w // 2)
         return offs, p
 
+    def _sub_streams(self, h, w, ny, sub_channels=None):
+        """(sub-streams per image and modality, symbols per sub-stream) of the y latents."""
+        if self.stream_layout == "single" and sub_channels is None:
+            return 1, ny
+        c = int(sub_channels or self.sub_channels)
+        if c < 1 or any(g % c for g in self.slice_ch):
+            raise ValueError(f"sub_channels = {c} must divide every channel group {self.slice_ch}")
+        sublen = c * h * (w // 2)
+        return ny // sublen, sublen
+
     def _common_front(self, b, B, H, W):
         """image -> g_a -> h_a. Returns io views."""
         p = b.prog
@@ -532,13 +562,15 @@ class ELIC_united(nn.Module):
         offs, ny = self._chunk_offsets(h, w)
         st = {}
         # both modalities' y streams live in one [2B, ...] buffer so one launch can code all of them
-        ycap = ny + ny // 2 + 64
+        # y streams per image and modality: 1 (reference layout) or ny / sublen equal sub-streams (multi-stream layout)
+        nsub, sublen = self._sub_streams(h, w, ny)
+        ycap = sublen + sublen // 2 + 64
         zcap = nz + nz // 2 + 64
         ysym_all, yidx_all = b.raw((2 * B, ny), torch.int32), b.raw((2 * B, ny), torch.uint8)
-        yout_all, zout_all = b.raw((2 * B, ycap), torch.int32), b.raw((2 * B, zcap), torch.int32)
-        # word counts of the 4B streams in gather order [y_r | y_d | z_r | z_d] (rgbd_gather_streams)
-        counts = b.raw((4 * B,), torch.int32)
-        ynw_all = counts[:2 * B]
+        yout_all, zout_all = b.raw((2 * B * nsub, ycap), torch.int32), b.raw((2 * B, zcap), torch.int32)
+        # word counts of all streams in gather order [y_r | y_d | z_r | z_d] (rgbd_gather_streams)
+        counts = b.raw((2 * B * nsub + 2 * B,), torch.int32)
+        ynw_all = counts[:2 * B * nsub]
         for k, which in enumerate(("r", "d")):
             eb = self._eb(which)
             med = self._dev32(("med", which), eb.medians)
@@ -547,9 +579,9 @@ class ELIC_united(nn.Module):
                 ysym=ysym_all[k * B:(k + 1) * B], yidx=yidx_all[k * B:(k + 1) * B],
                 zcap=zcap, ycap=ycap)
             s["zout"] = zout_all[k * B:(k + 1) * B]
-            s["yout"] = yout_all[k * B:(k + 1) * B]
-            s["znw"] = counts[(2 + k) * B:(3 + k) * B]
-            s["ynw"] = ynw_all[k * B:(k + 1) * B]
+            s["yout"] = yout_all[k * B * nsub:(k + 1) * B * nsub]
+            s["znw"] = counts[2 * B * nsub + k * B:2 * B * nsub + (k + 1) * B]
+            s["ynw"] = ynw_all[k * B * nsub:(k + 1) * B * nsub]
             st[which] = s
             zh = zcat.sub(0 if which == "r" else Nz, Nz)
             b.op("rgbd_eb_quantize", zs[which].ptr(), zs[which].cstride, B, hz * wz, Nz, med.data_ptr(),
@@ -585,25 +617,29 @@ class ELIC_united(nn.Module):
         same_tables = all(torch.equal(getattr(gr, n), getattr(gd, n)) for n in ("_quantized_cdf", "_cdf_length", "_offset"))
         if same_tables:   # the usual case: both Gaussian conditionals use get_scale_table()
             t = self._tables("gc", "r")
-            b.op("rgbd_rans_encode", ysym_all.data_ptr(), yidx_all.data_ptr(), ny, ny, 2 * B, ctypes.byref(t.struct),
-                 yout_all.data_ptr(), ycap, ynw_all.data_ptr())
+            # (the symbols of all images and both modalities are contiguous: 2B * nsub streams of sublen symbols)
+            b.op("rgbd_rans_encode", ysym_all.data_ptr(), yidx_all.data_ptr(), sublen, sublen, 2 * B * nsub,
+                 ctypes.byref(t.struct), yout_all.data_ptr(), ycap, ynw_all.data_ptr())
             p.keep.append(t)
         else:
             for which in ("r", "d"):
                 s = st[which]
                 t = self._tables("gc", which)
-                b.op("rgbd_rans_encode", s["ysym"].data_ptr(), s["yidx"].data_ptr(), ny, ny, B, ctypes.byref(t.struct),
-                     s["yout"].data_ptr(), s["ycap"], s["ynw"].data_ptr())
+                b.op("rgbd_rans_encode", s["ysym"].data_ptr(), s["yidx"].data_ptr(), sublen, sublen, B * nsub,
+                     ctypes.byref(t.struct), s["yout"].data_ptr(), s["ycap"], s["ynw"].data_ptr())
                 p.keep.append(t)
         # all stream tails packed into one pinned host buffer by one kernel: [4B counts | words ...]; sized for
         # 8 bits per symbol on average (a longer job falls back to per-stream copies in _collect_strings)
-        gcap = 2 * B * (ny + nz) // 4 + 64
-        p.io.update(st=st, shape=(hz, wz), y=ys, z=zs, yhat=yhat, ny=ny, nz=nz, counts=counts, gather_cap=gcap,
-                    gather_args=(yout_all.data_ptr(), ycap, 2 * B, zout_all.data_ptr(), zcap, 2 * B,
+        gcap = 2 * B * (ny + nz) // 4 + 64 + 4 * B * nsub
+        p.io.update(st=st, shape=(hz, wz), y=ys, z=zs, yhat=yhat, ny=ny, nz=nz, counts=counts, gather_cap=gcap, nsub=nsub,
+                    sublen=sublen, n_streams=2 * B * nsub + 2 * B,
+                    gather_args=(yout_all.data_ptr(), ycap, 2 * B * nsub, zout_all.data_ptr(), zcap, 2 * B,
                                  counts.data_ptr()))
         return p
 
-    def _build_decoder(self, B, hz, wz):
+    def _build_decoder(self, B, hz, wz, sub_channels=0):
+        """sub_channels = 0: the reference's single-stream layout; else the multi-stream layout with that many channels
+        per sub-stream."""
         b = Builder(self.device, self.act_dtype, self.tensor_cores and self.precision == "bf16")
         p = b.prog
         b.stage = "coder"
@@ -612,22 +648,25 @@ class ELIC_united(nn.Module):
         H, W = h * 16, w * 16
         nz = Nz * hz * wz
         offs, ny = self._chunk_offsets(h, w)
+        nsub, sublen = self._sub_streams(h, w, ny, sub_channels) if sub_channels else (1, ny)
         zcat = b.alloc(B, hz, wz, 3 * Nz)
-        # stream table: 4*B streams in the order [z_r | z_d | y_r | y_d], each B long
-        words_cap = 2 * B * ((nz + nz // 2 + 64) + (ny + ny // 2 + 64))
+        # stream table: the order is [z_r | z_d | y_r | y_d]; z: B streams per modality, y: B * nsub
+        n_streams = 2 * B + 2 * B * nsub
+        words_cap = 2 * B * ((nz + nz // 2 + 64) + nsub * (sublen + sublen // 2 + 64))
         words = b.raw((words_cap,), torch.int32)
-        word_off = b.raw((4 * B,), torch.int64)
-        word_len = b.raw((4 * B,), torch.int64)
-        state = b.raw((4 * B, 2), torch.int64)
-        p.io.update(words=words, word_off=word_off, word_len=word_len, words_cap=words_cap, state=state)
-        b.op("rgbd_rans_decode_init", words.data_ptr(), word_off.data_ptr(), 4 * B, state.data_ptr())
+        word_off = b.raw((n_streams,), torch.int64)
+        word_len = b.raw((n_streams,), torch.int64)
+        state = b.raw((n_streams, 2), torch.int64)
+        p.io.update(words=words, word_off=word_off, word_len=word_len, words_cap=words_cap, state=state, nsub=nsub,
+                    n_streams=n_streams)
+        b.op("rgbd_rans_decode_init", words.data_ptr(), word_off.data_ptr(), n_streams, state.data_ptr())
         st = {}
         for k, which in enumerate(("r", "d")):
             eb = self._eb(which)
             med = self._dev32(("med", which), eb.medians)
             s = dict(zsym=b.raw((B, nz), torch.int32), zidx=b.raw((B, nz), torch.uint8),
                      ysym=b.raw((B, ny), torch.int32), yidx=b.raw((B, ny), torch.uint8),
-                     zslot=k * B, yslot=(2 + k) * B)
+                     zslot=k * B, yslot=2 * B + k * B * nsub)
             st[which] = s
             chan = torch.arange(Nz, device=self.device, dtype=torch.uint8).repeat_interleave(hz * wz).repeat(B, 1)
             s["zidx"].copy_(chan)   # EntropyBottleneck._build_indexes (entropy_models.py:430-435)
@@ -659,9 +698,15 @@ class ELIC_united(nn.Module):
             b.stage = "coder"
             b.op("rgbd_ckbd_index", params.ptr(), table[which].data_ptr(), table[which].numel(), bound[which],
                  B, h, w, g, parity, s["yidx"].data_ptr(), ny, off)
-            b.op("rgbd_rans_decode_chunk", words.data_ptr(), word_off[s["yslot"]:].data_ptr(),
-                 word_len[s["yslot"]:].data_ptr(), B, state[s["yslot"]:].data_ptr(), s["yidx"].data_ptr(),
-                 s["ysym"].data_ptr(), ny, off, n, ctypes.byref(t.struct))
+            if nsub == 1:
+                b.op("rgbd_rans_decode_chunk", words.data_ptr(), word_off[s["yslot"]:].data_ptr(),
+                     word_len[s["yslot"]:].data_ptr(), B, state[s["yslot"]:].data_ptr(), s["yidx"].data_ptr(),
+                     s["ysym"].data_ptr(), ny, off, n, ctypes.byref(t.struct))
+            else:
+                # this step's n / sublen sub-streams of every image, all concurrently (fresh decoder state each)
+                b.op("rgbd_rans_decode_streams", words.data_ptr(), word_off.data_ptr(), word_len.data_ptr(), B, n // sublen,
+                     s["yslot"] + off // sublen, nsub, state.data_ptr(), s["yidx"].data_ptr(), s["ysym"].data_ptr(), ny,
+                     sublen, off, sublen, ctypes.byref(t.struct))
             b.op("rgbd_ckbd_dequant_scatter", s["ysym"].data_ptr(), ny, off, params.ptr(), B, h, w, g, parity,
                  yhat[which].ptr(), _DT[yhat[which].dtype], yhat[which].cstride, coff)
             p.keep.append(t)
@@ -730,7 +775,10 @@ class ELIC_united(nn.Module):
         return p
 
     def _program(self, kind, *dims, slot=0):
-        key = (kind, self.precision, self.tensor_cores, slot) + tuple(dims)
+        if kind == "decoder" and len(dims) == 3:
+            dims = tuple(dims) + (0,)          # (B, hz, wz, sub_channels): 0 = the reference's single-stream layout
+        layout = (self.stream_layout, self.sub_channels) if kind == "encoder" else None
+        key = (kind, self.precision, self.tensor_cores, self.fuse_blocks, layout, slot) + tuple(dims)
         if key not in self._programs:
             self._require_cuda()
             with torch.cuda.device(self.device), torch.no_grad():
@@ -795,8 +843,8 @@ class ELIC_united(nn.Module):
             p.io["depth"].copy_(depth, non_blocking=True)
             p.run(self.use_cuda_graph)
             if "gather_host" not in p.io:
-                p.io["gather_host"] = torch.empty((4 * B + p.io["gather_cap"],), dtype=torch.int32, device="cpu",
-                                                  pin_memory=True)
+                p.io["gather_host"] = torch.empty((p.io["n_streams"] + p.io["gather_cap"],), dtype=torch.int32,
+                                                  device="cpu", pin_memory=True)
             gh = p.io["gather_host"]
             # one kernel packs the counts and every stream's tail straight into pinned host memory (zero-copy
             # stores over PCIe): the strings are complete on the host when `done` fires, no second D2H round trip
@@ -828,13 +876,14 @@ class ELIC_united(nn.Module):
         """Cut the packed host buffer [4B counts | words] (rgbd_gather_streams) into the per-stream strings."""
         st = p.io["st"]
         host = gh.numpy()
-        counts = host[:4 * B].copy()
+        ns, nsub = p.io["n_streams"], p.io["nsub"]
+        counts = host[:ns].copy()
         if (counts < 0).any():
             raise L.RgbdError("rANS output buffer overflow (stream longer than 48 bits/symbol)")
         res = {"ry": [], "rz": [], "dy": [], "dz": []}
-        order = [(k, i) for k in ("ry", "dy", "rz", "dz") for i in range(B)]
+        order = [(k, i) for k in ("ry", "dy") for i in range(B * nsub)] + [(k, i) for k in ("rz", "dz") for i in range(B)]
         if int(counts.sum()) <= p.io["gather_cap"]:
-            words = host[4 * B:]
+            words = host[ns:]
             pos = 0
             for (key, _), n in zip(order, counts):
                 res[key].append(words[pos:pos + n].tobytes())
@@ -864,12 +913,21 @@ class ELIC_united(nn.Module):
         rz, dz = list(rgb_strings[1]), list(depth_strings[1])
         B = len(rz)
         ry, dy = list(rgb_strings[0]), list(depth_strings[0])
-        if len(ry) != B or len(dy) != B or len(dz) != B:
-            raise ValueError(f"expected {B} y strings per modality (one per image), got {len(ry)} / {len(dy)}")
+        if B == 0 or len(dz) != B or len(ry) != len(dy) or len(ry) % B:
+            raise ValueError(f"expected the same number of y strings per modality, a multiple of the {B} z strings; "
+                             f"got {len(ry)} / {len(dy)}")
         hz, wz = int(shape[0]), int(shape[1])
         if not (2 <= hz <= 1024 and 2 <= wz <= 1024):
             raise ValueError(f"latent shape {(hz, wz)} out of range (images of 128 .. 65536 pixels per side)")
-        p = self._program("decoder", B, hz, wz, slot=slot)
+        # one y string per image = the reference's layout; more = the multi-stream layout, whose sub-stream size follows
+        # from the count (2 M / sub_channels strings per image: both checkerboard halves of every channel group)
+        sub_channels = 0
+        if len(ry) != B:
+            per_image = len(ry) // B
+            if (2 * self.M) % per_image:
+                raise ValueError(f"{per_image} y strings per image do not form a multi-stream layout of {self.M} channels")
+            sub_channels = 2 * self.M // per_image
+        p = self._program("decoder", B, hz, wz, sub_channels, slot=slot)
         streams = rz + dz + ry + dy
         lens = np.array([len(s) // 4 for s in streams], dtype=np.int64)
         if any(len(s) % 4 or len(s) < 8 for s in streams):
@@ -881,7 +939,7 @@ class ELIC_united(nn.Module):
             raise ValueError("streams larger than the decoder's word buffer")
         if "words_host" not in p.io:   # pinned staging so the H2D copies are asynchronous
             p.io["words_host"] = torch.empty(p.io["words_cap"], dtype=torch.int32, device="cpu", pin_memory=True)
-            p.io["meta_host"] = torch.empty((2, 4 * B), dtype=torch.int64, device="cpu", pin_memory=True)
+            p.io["meta_host"] = torch.empty((2, p.io["n_streams"]), dtype=torch.int64, device="cpu", pin_memory=True)
         stream = self._slot_stream(slot)
         with torch.cuda.device(self.device), torch.cuda.stream(stream):
             prev = p.io.get("h2d_done")
@@ -903,7 +961,7 @@ class ELIC_united(nn.Module):
             p.io["h2d_done"] = ev
             p.run(self.use_cuda_graph)
             if "state_host" not in p.io:
-                p.io["state_host"] = torch.empty((4 * B, 2), dtype=torch.int64, device="cpu", pin_memory=True)
+                p.io["state_host"] = torch.empty((p.io["n_streams"], 2), dtype=torch.int64, device="cpu", pin_memory=True)
             p.io["state_host"].copy_(p.io["state"], non_blocking=True)
             done = torch.cuda.Event()
             done.record(stream)

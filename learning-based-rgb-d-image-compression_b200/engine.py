@@ -144,6 +144,20 @@ class PackedConv:
             self._wtc_shuffle = w.to(torch.bfloat16).contiguous()
         return self._wtc_shuffle
 
+    @property
+    def wtc_rb3x3(self):
+        """The 3x3 (96 -> 96) of a bottleneck block for rgbd_rb_*: bf16 [14 planes][96][64].  Plane t < 9 = tap t, input
+        channels 0-63; plane 9 + i = input channels 64-95 of tap 2 i in elements [0, 32) and of tap 2 i + 1 in [32, 64)."""
+        if getattr(self, "_wtc_rb", None) is None:
+            assert not self.transposed and self.k == 3 and self.stride == 1 and self.pad == 1 and self.Cin == 96 and self.Cout == 96
+            w = self.w32[:, :, :96].permute(0, 2, 1)         # [tap][co][ci]
+            planes = torch.zeros(14, 96, 64, device=self.w32.device, dtype=torch.float32)
+            planes[:9] = w[:, :, :64]
+            for t in range(9):
+                planes[9 + t // 2, :, 32 * (t % 2):32 * (t % 2) + 32] = w[t, :, 64:96]
+            self._wtc_rb = planes.to(torch.bfloat16).contiguous()
+        return self._wtc_rb
+
     def launches(self, H, W):
         """-> (Ho, Wo, [dict(Hs, Ws, o_step, o_off_y, o_off_x, i_step, taps=[(dy, dx, wtap)])])"""
         k, s, p = self.k, self.stride, self.pad
@@ -180,6 +194,7 @@ class Program:
         self.graph_launches = 0
         self.flops = 0      # dense conv flops of one run (MAC * 2)
         self.tc_plans = []  # rgbd_conv_tc_plan handles owned by this program
+        self.rb_plans = []  # rgbd_rb_plan handles (fused bottleneck blocks)
         self.n_tc = 0
         self.n_simt = 0
 
@@ -188,6 +203,8 @@ class Program:
             lib = L.load()
             for h in self.tc_plans:
                 lib.rgbd_conv_tc_plan_destroy(h)
+            for h in self.rb_plans:
+                lib.rgbd_rb_plan_destroy(h)
         except Exception:
             pass
 
@@ -429,6 +446,47 @@ class Builder:
         self.prog.keep.extend([pc, x.buf, out.buf])
         if scaled is not None:
             self.release(scaled)
+        return out
+
+    def can_fuse_block(self, pc1, pc2, pc3, x):
+        """1x1 (Cin -> 96) / 3x3 (96 -> 96) / 1x1 (96 -> 192) on a bf16 tensor-core plan: the shapes rgbd_rb_* takes."""
+        return (self.tensor_cores and x.dtype == torch.bfloat16 and not pc1.transposed and pc1.k == 1 and pc3.k == 1
+                and pc2.k == 3 and pc2.stride == 1 and pc2.pad == 1 and pc1.Cout == 96 and pc2.Cin == 96 and pc2.Cout == 96
+                and pc3.Cin == 96 and pc3.Cout == 192 and pc1.Cin % 64 == 0 and x.cstride % 8 == 0 and x.coff % 8 == 0
+                and x.H >= 2 and x.W >= 2)
+
+    def fused_block(self, pc1, pc2, pc3, x, res, out=None, final_relu=False):
+        """y = act(res + conv1x1(relu(conv3x3(relu(conv1x1(x))))) in one launch (csrc/conv_rb.cu): the bottleneck's two
+        96-channel intermediates never reach HBM."""
+        assert x.C == pc1.Cin and (res.N, res.H, res.W, res.C) == (x.N, x.H, x.W, pc3.Cout) and res.dtype == x.dtype
+        if out is None:
+            out = self.alloc(x.N, x.H, x.W, pc3.Cout, x.dtype)
+        assert (out.N, out.H, out.W, out.C) == (x.N, x.H, x.W, pc3.Cout) and out.dtype == x.dtype
+        d = L.RbDesc()
+        w1, w2, w3 = pc1.wtc, pc2.wtc_rb3x3, pc3.wtc
+        assert pc1.cin_pad == pc1.Cin and pc3.cin_pad == 128
+        d.x, d.res, d.y = x.ptr(), res.ptr(), out.ptr()
+        d.w1, d.w2, d.w3 = w1.data_ptr(), w2.data_ptr(), w3.data_ptr()
+        for name, pc in (("b1", pc1), ("b2", pc2), ("b3", pc3)):
+            setattr(d, name, pc.bias.data_ptr() if pc.bias is not None else None)
+        d.N, d.H, d.W = x.N, x.H, x.W
+        d.Cin, d.x_cstride, d.x_coff = x.C, x.cstride, x.coff
+        d.Cmid, d.Cout = 96, pc3.Cout
+        d.res_cstride, d.res_coff, d.y_cstride, d.y_coff = res.cstride, res.coff, out.cstride, out.coff
+        d.final_relu = int(bool(final_relu))
+        handle = C.c_void_p()
+        L.check(L.load().rgbd_rb_plan_create(C.byref(d), C.byref(handle)), "rgbd_rb_plan_create")
+        self.prog.rb_plans.append(handle)
+        run = self.op("rgbd_rb_run", handle)
+        self.prog.n_tc += 1
+        run.is_conv = True
+        run.is_tc = True
+        run.label = f"tc fused 1x1-3x3-1x1 {x.C}->96->96->{pc3.Cout} @{x.H}x{x.W}"
+        px = x.N * x.H * x.W
+        run.flops = 2 * px * (x.C * 96 + 9 * 96 * 96 + 96 * pc3.Cout)
+        self.prog.flops += run.flops
+        run.bytes = px * (x.C + 2 * pc3.Cout) * 2 + (x.C * 96 + 9 * 96 * 96 + 96 * pc3.Cout) * 2
+        self.prog.keep.extend([d, pc1, pc2, pc3, w1, w2, w3, x.buf, res.buf, out.buf])
         return out
 
     def se_scale(self, x, w1, w2, plus_one):

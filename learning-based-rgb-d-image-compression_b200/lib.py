@@ -42,6 +42,20 @@ class ConvDesc(C.Structure):
     ]
 
 
+class RbDesc(C.Structure):
+    """rgbd_rb_desc (include/rgbd_b200.h)"""
+    _fields_ = [
+        ("x", C.c_void_p), ("res", C.c_void_p), ("y", C.c_void_p),
+        ("w1", C.c_void_p), ("w2", C.c_void_p), ("w3", C.c_void_p),
+        ("b1", C.c_void_p), ("b2", C.c_void_p), ("b3", C.c_void_p),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("Cin", C.c_int32), ("x_cstride", C.c_int32), ("x_coff", C.c_int32),
+        ("Cmid", C.c_int32), ("Cout", C.c_int32),
+        ("res_cstride", C.c_int32), ("res_coff", C.c_int32), ("y_cstride", C.c_int32), ("y_coff", C.c_int32),
+        ("final_relu", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
 class RansTables(C.Structure):
     _fields_ = [
         ("cdf", C.c_void_p), ("base", C.c_void_p), ("length", C.c_void_p), ("offset", C.c_void_p),
@@ -57,6 +71,8 @@ _PROTOS = {
     "rgbd_conv_validate": [C.POINTER(ConvDesc)],
     "rgbd_conv_tc_plan_create": [C.POINTER(ConvDesc), _i32, C.POINTER(_vp)],
     "rgbd_conv_tc_run": [_vp, _vp],
+    "rgbd_rb_plan_create": [C.POINTER(RbDesc), C.POINTER(_vp)],
+    "rgbd_rb_run": [_vp, _vp],
     "rgbd_se_scale": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp],
     "rgbd_maxpool7s3": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_nchw_to_nhwc": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -79,12 +95,14 @@ _PROTOS = {
     "rgbd_gather_streams": [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _vp],
     "rgbd_rans_decode_init": [_vp, _vp, _i32, _vp, _vp],
     "rgbd_rans_decode_chunk": [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i32, C.POINTER(RansTables), _vp],
+    "rgbd_rans_decode_streams": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i32,
+                                 C.POINTER(RansTables), _vp],
     "rgbd_pmf_to_quantized_cdf": [_vp, _i32, _i32, _vp],
 }
 
 # every symbol include/rgbd_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = sorted(list(_PROTOS.keys()) + ["rgbd_last_error", "rgbd_abi_version", "rgbd_launch_count", "rgbd_count_launch",
-                                          "rgbd_conv_tc_plan_destroy"])
+                                          "rgbd_conv_tc_plan_destroy", "rgbd_rb_plan_destroy"])
 EXPORTS.remove("rgbd_conv_validate")
 
 _lib = None
@@ -113,6 +131,8 @@ def load():
     lib.rgbd_count_launch.argtypes = [C.c_int]
     lib.rgbd_conv_tc_plan_destroy.restype = None
     lib.rgbd_conv_tc_plan_destroy.argtypes = [_vp]
+    lib.rgbd_rb_plan_destroy.restype = None
+    lib.rgbd_rb_plan_destroy.argtypes = [_vp]
     _lib = lib
     return lib
 

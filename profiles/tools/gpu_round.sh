@@ -5,7 +5,11 @@ TAG=${1:-r02}; shift
 STEPS=${@:-tests smoke bench ref ncu sanitize}
 OUT=gpurun_out; mkdir -p $OUT
 for s in $STEPS; do case $s in
-tests)   timeout 1500 python -m pytest tests -m gpu -x -q -s > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -5 $OUT/${TAG}_tests.log; grep "\[parity" $OUT/${TAG}_tests.log;;
+tests)   : > $OUT/${TAG}_tests.log
+         for f in tests/test_gpu_*.py; do   # one process per file: a device-side trap in one file must not take the others down
+           timeout 1500 python -m pytest $f -m gpu -q -s >> $OUT/${TAG}_tests.log 2>&1; echo "$f rc=$?"
+         done
+         grep -E "passed|failed|error" $OUT/${TAG}_tests.log | tail -12; grep -E "^FAILED|^ERROR" $OUT/${TAG}_tests.log | head -20; grep "\[parity" $OUT/${TAG}_tests.log;;
 smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/${TAG}_smoke.log;;
 bench)   timeout 900 python bench.py --steps 4 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; tail -c 4000 $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err;;
 ref)     timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2>&1; echo "ref rc=$?"; tail -c 1500 $OUT/${TAG}_bench_ref.json;;
