@@ -192,6 +192,30 @@ int rgbd_cast_view_bf16(const float *x, void *y, int64_t npix, int32_t C, int32_
 int rgbd_zero(void *p, int64_t bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Metrics and image export next to the path (testing/tester_united.py:92-123, utils/metrics.py:8-14).
+ * ------------------------------------------------------------------------------------------ */
+/* out[n] = sum over one image's n_per_image elements of (a - b)^2 (double; inputs clamped to [0, 1] first when clamp01),
+ * the MSE of compute_metrics (utils/metrics.py:9-12).  work: N * n_part doubles; fixed summation order. */
+int rgbd_sq_error_sums(const float *a, const float *b, int32_t N, int64_t n_per_image, int32_t clamp01, double *work,
+                       int32_t n_part, double *out, void *stream);
+/* One level of pytorch_msssim's _ssim (v1.0.0, the package utils/metrics.py:5 imports; not vendored by the reference):
+ * 11-tap Gaussian window (sigma 1.5) applied separably without padding to x, y, x^2, y^2, xy of every [H, W] plane,
+ * K = (0.01, 0.03); sums[plane] = {sum of ssim_map, sum of cs_map} over the (H - 10) x (W - 10) valid positions.
+ * work: rgbd_ssim_work_elems(planes, H, W) doubles. */
+int rgbd_ssim_level(const float *x, const float *y, int32_t planes, int32_t H, int32_t W, float data_range, int32_t clamp01,
+                    double *work, double *sums, void *stream);
+int64_t rgbd_ssim_work_elems(int32_t planes, int32_t H, int32_t W);
+/* F.avg_pool2d(x, 2, padding = (H % 2, W % 2)) between MS-SSIM levels: y is [planes, (H + 1) / 2, (W + 1) / 2]. */
+int rgbd_avgpool2(const float *x, float *y, int32_t planes, int32_t H, int32_t W, int32_t clamp01, void *stream);
+/* saveImg (utils/IOutils.py:100-102): clamp to [0, 1], * 255, truncate -> interleaved u8 [N, crop_h, crop_w, C] of the
+ * top-left crop (crop0, dataset/utils.py:84-85) of an NCHW fp32 image. */
+int rgbd_quantize_u8(const float *x, uint8_t *y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t crop_h, int32_t crop_w,
+                     void *stream);
+/* 16-bit depth export (testing/tester_united.py:101-108): (x * scale).astype(uint16) of a [N, 1, H, W] image, cropped. */
+int rgbd_quantize_u16(const float *x, uint16_t *y, int32_t N, int32_t H, int32_t W, int32_t crop_h, int32_t crop_w,
+                      float scale, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Gaussian-conditional entropy model, checkerboard-fused.
  * ------------------------------------------------------------------------------------------ */
 /* One anchor / non-anchor coding step of the encoder: utils/ckbd.py:83-105 fused with

@@ -24,6 +24,7 @@ def install(reference_root, compressai_root=None):
     import models  # the reference's package
     models.modelZoo["ELIC_united_R2D"] = rgbd_b200.ELIC_united_R2D
     models.modelZoo["ELIC_united"] = rgbd_b200.ELIC_united
+    models.modelZoo["ELIC"] = rgbd_b200.ELIC            # single-modality baselines (testing/tester_single.py)
     return models.modelZoo
 
 

@@ -1,0 +1,573 @@
+"""ELIC — the single-modality codec (rgb-only / depth-only baselines) of the reference, B200-native.
+
+Same constructor, state_dict keys and API surface as the reference (models/elic.py:15-351), driven by
+testing/tester_single.py:38-64,121-163:
+
+    net = ELIC(config=Config(N, M, slice_num, slice_ch, quant), channel=3 | 1).eval()
+    net.load_state_dict(ckpt["state_dict"]); net.update(force=True); net.to("cuda")
+    out  = net(x)                                  # {"x_hat", "likelihoods": {"y_likelihoods", "z_likelihoods"}}   (:59-172)
+    code = net.compress(x)                         # {"strings": [[y], [z_0 .. z_{B-1}]], "shape"}                  (:174-246)
+    rec  = net.decompress(code["strings"], code["shape"])      # {"x_hat", "cost_time"}                            (:248-330)
+
+It is a strict subset of what ELIC_united needs, so it is compiled into launches of the same kernels: the g_a / g_s
+walker, the fused bottleneck blocks, the checkerboard quantise / index kernels and the rANS coder; the graph pieces that do
+not depend on the number of modalities are borrowed from ELIC_united as plain functions.  Differences to the united model
+that matter here: the entropy-parameter network is three 1x1 convs without the SE gate (modules/transform/entropy.py:7-28),
+h_s is a plain deconv chain with ReLU (modules/transform/synthesis.py:276-285), and the context order per step is
+[local, channel, hyper] (models/elic.py:88,117,133-135).
+
+For batch B > 1 the y entry holds B per-image strings (see elic_united.py); `stream_layout="multi"` is available as well.
+"""
+import ctypes
+import os
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import lib as L
+from .elic_united import ELIC_united, _DecompressHandle
+from .engine import Builder, _DT
+from .entropy_models import EntropyBottleneck, GaussianConditional, get_scale_table
+from .modules import AttentionBlock, ChannelContextEX, ResidualBottleneck, _chain, conv, deconv
+
+RELU, NONE = L.ACT_RELU, L.ACT_NONE
+
+
+class EntropyParameters(nn.Module):
+    """modules/transform/entropy.py:7-28: 1x1 (in -> out*5//3) act 1x1 (-> out*4//3) act 1x1 (-> out)."""
+
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.fusion = _chain(nn.Conv2d(in_dim, out_dim * 5 // 3, 1), nn.Conv2d(out_dim * 5 // 3, out_dim * 4 // 3, 1),
+                             nn.Conv2d(out_dim * 4 // 3, out_dim, 1))
+
+
+class _SeqHolder(nn.Module):
+    def __init__(self, name, seq):
+        super().__init__()
+        setattr(self, name, seq)
+
+
+class ELIC(nn.Module):
+    # graph pieces and plumbing shared with the two-modality model (they only touch self._packed / self._aux / flags)
+    _pc = ELIC_united._pc
+    _dev32 = ELIC_united._dev32
+    _rb = ELIC_united._rb
+    _ru = ELIC_united._ru
+    _attention = ELIC_united._attention
+    _channel_ctx = ELIC_united._channel_ctx
+    _sub_streams = ELIC_united._sub_streams
+    _chunk_offsets = ELIC_united._chunk_offsets
+    _slot_stream = ELIC_united._slot_stream
+    _order_after_producer = ELIC_united._order_after_producer
+    _program = ELIC_united._program
+    set_precision = ELIC_united.set_precision
+    count_parameters = ELIC_united.count_parameters
+    device = ELIC_united.device
+    act_dtype = ELIC_united.act_dtype
+
+    def __init__(self, config, channel=3, return_mid=False, **kwargs):
+        super().__init__()
+        if return_mid:
+            raise NotImplementedError("return_mid (the concat baseline's side outputs) is not part of this path")
+        N, M = config.N, config.M
+        self.N, self.M, self.channel = N, M, int(channel)
+        self.quant = config.quant
+        self.slice_num = config.slice_num
+        self.slice_ch = list(config.slice_ch)
+        assert sum(self.slice_ch) == M and len(self.slice_ch) == self.slice_num
+        sc = self.slice_ch
+        self.entropy_bottleneck = EntropyBottleneck(N)      # first: CompressionModel.__init__ creates it (priors.py:45-52)
+
+        def rb3():
+            return [ResidualBottleneck(N), ResidualBottleneck(N), ResidualBottleneck(N)]
+
+        self.g_a = _SeqHolder("analysis_transform", nn.Sequential(
+            conv(self.channel, N), *rb3(), conv(N, N), *rb3(), AttentionBlock(N), conv(N, N), *rb3(), conv(N, M),
+            AttentionBlock(M)))
+        self.g_s = _SeqHolder("synthesis_transform", nn.Sequential(
+            AttentionBlock(M), deconv(M, N), *rb3(), deconv(N, N), AttentionBlock(N), *rb3(), deconv(N, N), *rb3(),
+            deconv(N, self.channel)))
+        self.h_a = _SeqHolder("reduction", _chain(nn.Conv2d(M, N, 3, padding=1), conv(N, N), conv(N, N)))
+        self.h_s = _SeqHolder("increase", _chain(deconv(N, M), deconv(M, M * 3 // 2), deconv(M * 3 // 2, M * 2, k=3, s=1)))
+        self.local_context = nn.ModuleList(nn.Conv2d(c, 2 * c, 5, 1, 2) for c in sc)
+        self.channel_context = nn.ModuleList(
+            ChannelContextEX(sum(sc[:i]), sc[i] * 2) if i else None for i in range(self.slice_num))
+        self.entropy_parameters_anchor = nn.ModuleList(
+            EntropyParameters(2 * M + (2 * c if i else 0), 2 * c) for i, c in enumerate(sc))
+        self.entropy_parameters_nonanchor = nn.ModuleList(
+            EntropyParameters(2 * M + (4 * c if i else 2 * c), 2 * c) for i, c in enumerate(sc))
+        self.gaussian_conditional = GaussianConditional(None)
+
+        self.precision = kwargs.get("precision", "fp32")
+        self.use_cuda_graph = kwargs.get("cuda_graph", False)
+        self.tensor_cores = kwargs.get("tensor_cores", True)
+        self.fuse_blocks = kwargs.get("fuse_blocks", os.environ.get("RGBD_FUSE_BLOCKS", "1") != "0")
+        self.stream_layout = kwargs.get("stream_layout", "single")
+        self.sub_channels = int(kwargs.get("sub_channels", 4))
+        self._packed = None
+        self._programs = {}
+        self._aux = {}
+
+    # ------------------------------------------------------------------ reference API: tables / weights
+    def aux_loss(self):
+        raise NotImplementedError("training is out of scope of the B200 inference path")
+
+    def update(self, scale_table=None, force=False):
+        """models/elic.py:332-337"""
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = self.gaussian_conditional.update_scale_table(scale_table, force=force)
+        updated |= self.entropy_bottleneck.update(force=force)
+        self._invalidate()
+        return updated
+
+    def load_state_dict(self, state_dict, strict=True):
+        """models/elic.py:345-351 (strict load after resizing the CDF buffers to the checkpoint's sizes)."""
+        for name in ("gaussian_conditional", "entropy_bottleneck"):
+            mod = getattr(self, name)
+            bufs = ["_quantized_cdf", "_offset", "_cdf_length"] + (["scale_table"] if name == "gaussian_conditional" else [])
+            for bname in bufs:
+                key = f"{name}.{bname}"
+                if key in state_dict:
+                    cur = getattr(mod, bname)
+                    if cur.numel() == 0 or cur.shape != state_dict[key].shape:
+                        setattr(mod, bname, torch.empty(state_dict[key].shape, dtype=cur.dtype, device=cur.device))
+            mod.invalidate()
+        rv = super().load_state_dict(state_dict, strict=strict)
+        self._invalidate()
+        return rv
+
+    def _apply(self, fn, *a, **k):
+        rv = super()._apply(fn, *a, **k)
+        self._invalidate()
+        return rv
+
+    def _invalidate(self):
+        self._packed = None
+        self._programs = {}
+        self._aux = {}
+        self.__dict__.pop("_slot_streams", None)
+        self.gaussian_conditional.invalidate()
+        self.entropy_bottleneck.invalidate()
+
+    def _require_cuda(self):
+        L.load()
+        if self.device.type != "cuda":
+            raise L.RgbdError("ELIC runs on a CUDA device only (no CPU fallback); call .to('cuda')")
+        if self.gaussian_conditional.quantized_cdf.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+
+    def _check_input(self, x):
+        if x.dim() != 4 or x.shape[1] != self.channel:
+            raise ValueError(f"expected x [B,{self.channel},H,W]")
+        if x.shape[2] % 64 or x.shape[3] % 64:
+            raise ValueError("H and W must be multiples of 64 (pad first, dataset/utils.py:58-67)")
+        if x.shape[2] < 64 or x.shape[3] < 64:
+            raise ValueError("H and W must be >= 64")
+
+    # ------------------------------------------------------------------ graph
+    def _walk(self, b, seq, x, final_dtype=None):
+        """modules/transform/analysis.py:29-52, synthesis.py:32-51"""
+        n = len(seq)
+        first = x
+        for i, mod in enumerate(seq):
+            last = i == n - 1
+            if isinstance(mod, (nn.Conv2d, nn.ConvTranspose2d)):
+                s2d = x.C == 12 * mod.in_channels
+                pc = self._pc(mod, split3=s2d or x.C == 3 * mod.in_channels, s2d=s2d)
+                y = b.conv(pc, x, out_dtype=final_dtype if last else None)
+            elif isinstance(mod, ResidualBottleneck):
+                y = self._rb(b, mod, x)
+            elif isinstance(mod, AttentionBlock):
+                y = self._attention(b, mod, x, out_dtype=final_dtype if last else None)
+            else:
+                raise TypeError(type(mod))
+            if x is not first:
+                b.release(x)
+            x = y
+        return x
+
+    def _front(self, b, B, H, W):
+        p = b.prog
+        C = self.channel
+        split = 2 if b.tensor_cores else 0
+        b.stage = "io"
+        x = b.alloc(B, H // 2, W // 2, 12 * C) if split else b.alloc(B, H, W, C)
+        xin = b.raw((B, C, H, W), torch.float32)
+        p.io["x"] = xin
+        b.op("rgbd_nchw_to_nhwc", xin.data_ptr(), x.ptr(), _DT[x.dtype], B, C, H, W, x.cstride, x.coff, split)
+        b.stage = "g_a"
+        y = self._walk(b, self.g_a.analysis_transform, x, final_dtype=torch.float32)
+        b.stage = "h_a"
+        seq = self.h_a.reduction
+        if b.tensor_cores and y.dtype == torch.float32:
+            y16 = b.alloc(y.N, y.H, y.W, y.C, torch.bfloat16)
+            b.op("rgbd_cast_view_bf16", y.ptr(), y16.ptr(), y.N * y.H * y.W, y.C, y.cstride, y.coff, y16.cstride, y16.coff)
+            t1 = b.conv(self._pc(seq[0]), y16, act=RELU)
+            b.release(y16)
+        else:
+            t1 = b.conv(self._pc(seq[0]), y, act=RELU)
+        t2 = b.conv(self._pc(seq[2]), t1, act=RELU)
+        z = b.conv(self._pc(seq[4]), t2, out_dtype=torch.float32)
+        b.release(t1, t2)
+        b.stage = "coder"
+        return y, z
+
+    def _h_s(self, b, zhat, hyper):
+        """modules/transform/synthesis.py:276-285: deconv ReLU deconv ReLU deconv(k3 s1) -> the hyper slot of the context"""
+        seq = self.h_s.increase
+        t1 = b.conv(self._pc(seq[0]), zhat, act=RELU)
+        t2 = b.conv(self._pc(seq[2]), t1, act=RELU)
+        b.release(t1)
+        b.conv(self._pc(seq[4]), t2, out=hyper)
+        b.release(t2)
+
+    def _ctx_layout(self, idx):
+        """Our context buffer: [hyper 2M | ch 2g (idx > 0) | loc 2g]; the reference concatenates [loc, ch, hyper]
+        (models/elic.py:88,117,133-135), so the first 1x1 of every EntropyParameters gets its input channels permuted."""
+        M, g = self.M, self.slice_ch[idx]
+        has_ch = idx > 0
+        o = {"hyper": 0}
+        p = 2 * M
+        if has_ch:
+            o["ch"] = p
+            p += 2 * g
+        o["loc"] = p
+
+        def perm(ref_order, ours):
+            start, q = {}, 0
+            for name, width in ref_order:
+                start[name] = q
+                q += width
+            idxs = []
+            for name, width in ours:
+                idxs.extend(range(start[name], start[name] + width))
+            return torch.tensor(idxs, dtype=torch.long, device="cpu")
+
+        hy, ch, lo = ("hyper", 2 * M), ("ch", 2 * g), ("loc", 2 * g)
+        if has_ch:
+            plans = {"anchor": perm([ch, hy], [hy, ch]), "nonanchor": perm([lo, ch, hy], [hy, ch, lo])}
+        else:
+            plans = {"anchor": perm([hy], [hy]), "nonanchor": perm([lo, hy], [hy, lo])}
+        return o, plans
+
+    def _ep(self, b, m, x, perm, out):
+        t1 = b.conv(self._pc(m.fusion[0], in_perm=perm), x, act=RELU)
+        t2 = b.conv(self._pc(m.fusion[2]), t1, act=RELU)
+        b.release(t1)
+        b.conv(self._pc(m.fusion[4]), t2, out=out)
+        b.release(t2)
+
+    def _context_chain(self, b, ctx, yhat, code_step):
+        """models/elic.py:73-156 / 192-241 / 264-315: per channel group anchor then non-anchor."""
+        for idx, g in enumerate(self.slice_ch):
+            coff = sum(self.slice_ch[:idx])
+            o, perms = self._ctx_layout(idx)
+            params = b.alloc(ctx.N, ctx.H, ctx.W, 2 * g, torch.float32)
+            if idx > 0:
+                self._channel_ctx(b, self.channel_context[idx], yhat.sub(0, coff), ctx.sub(o["ch"], 2 * g))
+            self._ep(b, self.entropy_parameters_anchor[idx], ctx.sub(0, o["loc"]), perms["anchor"], params)
+            code_step(idx, 0, params, g, coff)
+            b.conv(self._pc(self.local_context[idx]), yhat.sub(coff, g), out=ctx.sub(o["loc"], 2 * g))
+            self._ep(b, self.entropy_parameters_nonanchor[idx], ctx.sub(0, o["loc"] + 2 * g), perms["nonanchor"], params)
+            code_step(idx, 1, params, g, coff)
+            b.release(params)
+
+    def _tables(self, which):
+        m = self.gaussian_conditional if which == "gc" else self.entropy_bottleneck
+        return m.device_tables(self.device)
+
+    def _chain_inputs(self, b, B, h, w):
+        M, gm = self.M, max(self.slice_ch)
+        ctx = b.alloc(B, h, w, 2 * M + 4 * gm)
+        yhat = b.alloc(B, h, w, M, zero=True)
+        b.op("rgbd_zero", yhat.buf.data_ptr(), yhat.buf.numel() * yhat.buf.element_size())
+        table = self._dev32(("scale_table",), lambda: self.gaussian_conditional.scale_table)
+        bound = float(self.gaussian_conditional.lower_bound_scale.bound)
+        return ctx, yhat, table, bound
+
+    def _build_encoder(self, B, H, W):
+        b = Builder(self.device, self.act_dtype, self.tensor_cores and self.precision == "bf16")
+        p = b.prog
+        y, z = self._front(b, B, H, W)
+        h, w, hz, wz = y.H, y.W, z.H, z.W
+        Nz, M = self.N, self.M
+        nz = Nz * hz * wz
+        offs, ny = self._chunk_offsets(h, w)
+        nsub, sublen = self._sub_streams(h, w, ny)
+        ycap, zcap = sublen + sublen // 2 + 64, nz + nz // 2 + 64
+        ysym, yidx = b.raw((B, ny), torch.int32), b.raw((B, ny), torch.uint8)
+        zsym, zidx = b.raw((B, nz), torch.int32), b.raw((B, nz), torch.uint8)
+        yout, zout = b.raw((B * nsub, ycap), torch.int32), b.raw((B, zcap), torch.int32)
+        counts = b.raw((B * nsub + B,), torch.int32)         # gather order [y | z]
+        med = self._dev32(("med",), self.entropy_bottleneck.medians)
+        zhat = b.alloc(B, hz, wz, Nz)
+        b.op("rgbd_eb_quantize", z.ptr(), z.cstride, B, hz * wz, Nz, med.data_ptr(), zsym.data_ptr(), zidx.data_ptr(),
+             zhat.ptr(), _DT[zhat.dtype], zhat.cstride, zhat.coff)
+        te = self._tables("eb")
+        b.op("rgbd_rans_encode", zsym.data_ptr(), zidx.data_ptr(), nz, nz, B, ctypes.byref(te.struct), zout.data_ptr(), zcap,
+             counts[B * nsub:].data_ptr())
+        b.stage = "h_s"
+        ctx, yhat, table, bound = self._chain_inputs(b, B, h, w)
+        self._h_s(b, zhat, ctx.sub(0, 2 * M))
+        b.stage = "chain"
+
+        def code_step(idx, parity, params, g, coff):
+            b.stage = "coder"
+            b.op("rgbd_ckbd_quantize_index", y.ptr(), y.cstride, y.coff + coff, params.ptr(), table.data_ptr(), table.numel(),
+                 bound, B, h, w, g, parity, ysym.data_ptr(), yidx.data_ptr(), ny, offs[(idx, parity)], yhat.ptr(),
+                 _DT[yhat.dtype], yhat.cstride, coff)
+            b.stage = "chain"
+
+        self._context_chain(b, ctx, yhat, code_step)
+        b.stage = "coder"
+        tg = self._tables("gc")
+        b.op("rgbd_rans_encode", ysym.data_ptr(), yidx.data_ptr(), sublen, sublen, B * nsub, ctypes.byref(tg.struct),
+             yout.data_ptr(), ycap, counts.data_ptr())
+        p.keep.extend([te, tg])
+        gcap = B * (ny + nz) // 4 + 64 + 2 * B * nsub
+        p.io.update(shape=(hz, wz), y=y, z=z, yhat=yhat, ny=ny, nz=nz, nsub=nsub, sublen=sublen, n_streams=B * nsub + B,
+                    ysym=ysym, yidx=yidx, zsym=zsym, zidx=zidx, yout=yout, zout=zout, ycap=ycap, zcap=zcap, gather_cap=gcap,
+                    gather_args=(yout.data_ptr(), ycap, B * nsub, zout.data_ptr(), zcap, B, counts.data_ptr()))
+        return p
+
+    def _build_decoder(self, B, hz, wz, sub_channels=0):
+        b = Builder(self.device, self.act_dtype, self.tensor_cores and self.precision == "bf16")
+        p = b.prog
+        b.stage = "coder"
+        Nz, M, C = self.N, self.M, self.channel
+        h, w = hz * 4, wz * 4
+        H, W = h * 16, w * 16
+        nz = Nz * hz * wz
+        offs, ny = self._chunk_offsets(h, w)
+        nsub, sublen = self._sub_streams(h, w, ny, sub_channels) if sub_channels else (1, ny)
+        n_streams = B + B * nsub                                   # [z | y]
+        words_cap = B * ((nz + nz // 2 + 64) + nsub * (sublen + sublen // 2 + 64))
+        words = b.raw((words_cap,), torch.int32)
+        word_off, word_len = b.raw((n_streams,), torch.int64), b.raw((n_streams,), torch.int64)
+        state = b.raw((n_streams, 2), torch.int64)
+        p.io.update(words=words, word_off=word_off, word_len=word_len, words_cap=words_cap, state=state, nsub=nsub,
+                    n_streams=n_streams)
+        b.op("rgbd_rans_decode_init", words.data_ptr(), word_off.data_ptr(), n_streams, state.data_ptr())
+        zsym, zidx = b.raw((B, nz), torch.int32), b.raw((B, nz), torch.uint8)
+        ysym, yidx = b.raw((B, ny), torch.int32), b.raw((B, ny), torch.uint8)
+        zidx.copy_(torch.arange(Nz, device=self.device, dtype=torch.uint8).repeat_interleave(hz * wz).repeat(B, 1))
+        te, tg = self._tables("eb"), self._tables("gc")
+        p.keep.extend([te, tg])
+        b.op("rgbd_rans_decode_chunk", words.data_ptr(), word_off.data_ptr(), word_len.data_ptr(), B, state.data_ptr(),
+             zidx.data_ptr(), zsym.data_ptr(), nz, 0, nz, ctypes.byref(te.struct))
+        med = self._dev32(("med",), self.entropy_bottleneck.medians)
+        zhat = b.alloc(B, hz, wz, Nz)
+        b.op("rgbd_eb_dequantize", zsym.data_ptr(), B, hz * wz, Nz, med.data_ptr(), zhat.ptr(), _DT[zhat.dtype], zhat.cstride,
+             zhat.coff)
+        b.stage = "h_s"
+        ctx, yhat, table, bound = self._chain_inputs(b, B, h, w)
+        self._h_s(b, zhat, ctx.sub(0, 2 * M))
+        b.stage = "chain"
+        yslot = B
+
+        def code_step(idx, parity, params, g, coff):
+            n = g * h * (w // 2)
+            off = offs[(idx, parity)]
+            b.stage = "coder"
+            b.op("rgbd_ckbd_index", params.ptr(), table.data_ptr(), table.numel(), bound, B, h, w, g, parity, yidx.data_ptr(),
+                 ny, off)
+            if nsub == 1:
+                b.op("rgbd_rans_decode_chunk", words.data_ptr(), word_off[yslot:].data_ptr(), word_len[yslot:].data_ptr(), B,
+                     state[yslot:].data_ptr(), yidx.data_ptr(), ysym.data_ptr(), ny, off, n, ctypes.byref(tg.struct))
+            else:
+                b.op("rgbd_rans_decode_streams", words.data_ptr(), word_off.data_ptr(), word_len.data_ptr(), B, n // sublen,
+                     yslot + off // sublen, nsub, state.data_ptr(), yidx.data_ptr(), ysym.data_ptr(), ny, sublen, off, sublen,
+                     ctypes.byref(tg.struct))
+            b.op("rgbd_ckbd_dequant_scatter", ysym.data_ptr(), ny, off, params.ptr(), B, h, w, g, parity, yhat.ptr(),
+                 _DT[yhat.dtype], yhat.cstride, coff)
+            b.stage = "chain"
+
+        self._context_chain(b, ctx, yhat, code_step)
+        b.stage = "g_s"
+        x = self._walk(b, self.g_s.synthesis_transform, yhat)
+        b.stage = "io"
+        out = b.raw((B, C, H, W), torch.float32)
+        b.op("rgbd_nhwc_to_nchw", x.ptr(), _DT[x.dtype], out.data_ptr(), B, C, H, W, x.cstride, x.coff, 0)
+        p.io.update(out=out, yhat=yhat, ny=ny, nz=nz, ysym=ysym, yidx=yidx, zsym=zsym)
+        return p
+
+    def _build_forward(self, B, H, W):
+        b = Builder(self.device, self.act_dtype, self.tensor_cores and self.precision == "bf16")
+        p = b.prog
+        y, z = self._front(b, B, H, W)
+        h, w, hz, wz = y.H, y.W, z.H, z.W
+        Nz, M, C = self.N, self.M, self.channel
+        eb = self.entropy_bottleneck
+        ebp = eb.packed_params(self.device)
+        p.keep.append(ebp)
+        lz, ly = b.raw((B, Nz, hz, wz), torch.float32), b.raw((B, M, h, w), torch.float32)
+        zhat = b.alloc(B, hz, wz, Nz)
+        b.op("rgbd_eb_likelihood", z.ptr(), z.cstride, B, hz * wz, Nz, ebp.data_ptr(), eb.likelihood_bound, zhat.ptr(),
+             _DT[zhat.dtype], zhat.cstride, zhat.coff, lz.data_ptr())
+        b.stage = "h_s"
+        ctx, yhat, table, bound = self._chain_inputs(b, B, h, w)
+        self._h_s(b, zhat, ctx.sub(0, 2 * M))
+        b.stage = "chain"
+        gc = self.gaussian_conditional
+
+        def code_step(idx, parity, params, g, coff):
+            b.op("rgbd_ckbd_ste_likelihood", y.ptr(), y.cstride, y.coff + coff, params.ptr(), bound, gc.likelihood_bound, B, h, w,
+                 g, parity, yhat.ptr(), _DT[yhat.dtype], yhat.cstride, coff, ly.data_ptr(), M, coff)
+
+        self._context_chain(b, ctx, yhat, code_step)
+        b.stage = "g_s"
+        x = self._walk(b, self.g_s.synthesis_transform, yhat)
+        b.stage = "io"
+        out = b.raw((B, C, H, W), torch.float32)
+        b.op("rgbd_nhwc_to_nchw", x.ptr(), _DT[x.dtype], out.data_ptr(), B, C, H, W, x.cstride, x.coff, 0)
+        p.io.update(out=out, ly=ly, lz=lz, y=y, z=z, yhat=yhat)
+        return p
+
+    # ------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def forward(self, x):
+        if self.quant != "ste":
+            raise NotImplementedError(f"forward() implements quant='ste' only (got {self.quant!r})")
+        self._check_input(x)
+        B, _, H, W = x.shape
+        p = self._program("forward", B, H, W)
+        with torch.cuda.device(self.device):
+            p.io["x"].copy_(x)
+            p.run(self.use_cuda_graph)
+        return {"x_hat": p.io["out"].clone(),
+                "likelihoods": {"y_likelihoods": p.io["ly"].clone(), "z_likelihoods": p.io["lz"].clone()}}
+
+    @torch.no_grad()
+    def compress(self, x):
+        return self.compress_async(x).result()
+
+    @torch.no_grad()
+    def compress_async(self, x, slot=0):
+        self._check_input(x)
+        B, _, H, W = x.shape
+        p = self._program("encoder", B, H, W, slot=slot)
+        stream = self._slot_stream(slot)
+        self._order_after_producer(stream, x)
+        with torch.cuda.device(self.device), torch.cuda.stream(stream):
+            p.io["x"].copy_(x, non_blocking=True)
+            p.run(self.use_cuda_graph)
+            if "gather_host" not in p.io:
+                p.io["gather_host"] = torch.empty((p.io["n_streams"] + p.io["gather_cap"],), dtype=torch.int32, device="cpu",
+                                                  pin_memory=True)
+            gh = p.io["gather_host"]
+            L.call("rgbd_gather_streams", *p.io["gather_args"], gh.data_ptr(), p.io["gather_cap"],
+                   ctypes.c_void_p(stream.cuda_stream))
+            done = torch.cuda.Event()
+            done.record(stream)
+        return _SingleCompressHandle(self, p, B, stream, done, gh)
+
+    def _collect(self, p, B, gh):
+        host = gh.numpy()
+        ns, nsub = p.io["n_streams"], p.io["nsub"]
+        counts = host[:ns].copy()
+        if (counts < 0).any():
+            raise L.RgbdError("rANS output buffer overflow (stream longer than 48 bits/symbol)")
+        ys, zs = [], []
+        if int(counts.sum()) <= p.io["gather_cap"]:
+            words, pos = host[ns:], 0
+            for i, n in enumerate(counts):
+                (ys if i < B * nsub else zs).append(words[pos:pos + n].tobytes())
+                pos += int(n)
+            return ys, zs
+        for i, n in enumerate(counts):
+            out, cap, j = (p.io["yout"], p.io["ycap"], i) if i < B * nsub else (p.io["zout"], p.io["zcap"], i - B * nsub)
+            (ys if i < B * nsub else zs).append(out[j, cap - int(n):].cpu().numpy().tobytes())
+        return ys, zs
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        self._require_cuda()
+        torch.cuda.synchronize(self.device)
+        t0 = time.process_time()
+        out = self.decompress_async(strings, shape).result()
+        torch.cuda.synchronize(self.device)
+        return {"x_hat": out["x_hat"], "cost_time": time.process_time() - t0}
+
+    @torch.no_grad()
+    def decompress_async(self, strings, shape, slot=0):
+        self._require_cuda()
+        ys, zs = list(strings[0]), list(strings[1])
+        B = len(zs)
+        if B == 0 or len(ys) % B:
+            raise ValueError(f"expected a multiple of the {B} z strings as y strings, got {len(ys)}")
+        hz, wz = int(shape[0]), int(shape[1])
+        if not (1 <= hz <= 1024 and 1 <= wz <= 1024):
+            raise ValueError(f"latent shape {(hz, wz)} out of range")
+        sub_channels = 0
+        if len(ys) != B:
+            per_image = len(ys) // B
+            if (2 * self.M) % per_image:
+                raise ValueError(f"{per_image} y strings per image do not form a multi-stream layout of {self.M} channels")
+            sub_channels = 2 * self.M // per_image
+        p = self._program("decoder", B, hz, wz, sub_channels, slot=slot)
+        streams = zs + ys
+        if any(len(s) % 4 or len(s) < 8 for s in streams):
+            raise ValueError("corrupt stream: rANS payloads are whole 32-bit words, at least two")
+        lens = np.array([len(s) // 4 for s in streams], dtype=np.int64)
+        offs = np.zeros_like(lens)
+        offs[1:] = np.cumsum(lens[:-1])
+        total = int(lens.sum())
+        if total > p.io["words_cap"]:
+            raise ValueError("streams larger than the decoder's word buffer")
+        if "words_host" not in p.io:
+            p.io["words_host"] = torch.empty(p.io["words_cap"], dtype=torch.int32, device="cpu", pin_memory=True)
+            p.io["meta_host"] = torch.empty((2, p.io["n_streams"]), dtype=torch.int64, device="cpu", pin_memory=True)
+            p.io["state_host"] = torch.empty((p.io["n_streams"], 2), dtype=torch.int64, device="cpu", pin_memory=True)
+        stream = self._slot_stream(slot)
+        with torch.cuda.device(self.device), torch.cuda.stream(stream):
+            prev = p.io.get("h2d_done")
+            if prev is not None:
+                prev.synchronize()
+            wh = p.io["words_host"].numpy()
+            pos = 0
+            for sbytes in streams:
+                n = len(sbytes) // 4
+                wh[pos:pos + n] = np.frombuffer(sbytes, dtype=np.int32)
+                pos += n
+            p.io["meta_host"][0].copy_(torch.from_numpy(offs))
+            p.io["meta_host"][1].copy_(torch.from_numpy(lens))
+            p.io["words"][:total].copy_(p.io["words_host"][:total], non_blocking=True)
+            p.io["word_off"].copy_(p.io["meta_host"][0], non_blocking=True)
+            p.io["word_len"].copy_(p.io["meta_host"][1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            p.io["h2d_done"] = ev
+            p.run(self.use_cuda_graph)
+            p.io["state_host"].copy_(p.io["state"], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(stream)
+        return _SingleDecompressHandle(p, stream, done, lens)
+
+
+class _SingleCompressHandle:
+    def __init__(self, net, prog, B, stream, done, gather_host):
+        self.net, self.prog, self.B, self.stream, self.done, self.gather_host = net, prog, B, stream, done, gather_host
+
+    def result(self):
+        self.done.synchronize()
+        ys, zs = self.net._collect(self.prog, self.B, self.gather_host)
+        return {"strings": [ys, zs], "shape": torch.Size(self.prog.io["shape"])}
+
+
+class _SingleDecompressHandle(_DecompressHandle):
+    def result(self, clone=True):
+        self.done.synchronize()
+        pos = self.prog.io["state_host"].numpy()[:, 1]
+        if (pos != self.word_lens).any():
+            bad = int(np.nonzero(pos != self.word_lens)[0][0])
+            raise ValueError(f"corrupt stream {bad}: decoder stopped at word {int(pos[bad])} of {int(self.word_lens[bad])}")
+        x = self.prog.io["out"]
+        if clone:
+            with torch.cuda.stream(self.stream):
+                x = x.clone()
+            self.stream.synchronize()
+        return {"x_hat": x}

@@ -97,12 +97,17 @@ _PROTOS = {
     "rgbd_rans_decode_chunk": [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i32, C.POINTER(RansTables), _vp],
     "rgbd_rans_decode_streams": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i32,
                                  C.POINTER(RansTables), _vp],
+    "rgbd_sq_error_sums": [_vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp],
+    "rgbd_ssim_level": [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp],
+    "rgbd_avgpool2": [_vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "rgbd_quantize_u8": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "rgbd_quantize_u16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "rgbd_pmf_to_quantized_cdf": [_vp, _i32, _i32, _vp],
 }
 
 # every symbol include/rgbd_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = sorted(list(_PROTOS.keys()) + ["rgbd_last_error", "rgbd_abi_version", "rgbd_launch_count", "rgbd_count_launch",
-                                          "rgbd_conv_tc_plan_destroy", "rgbd_rb_plan_destroy"])
+                                          "rgbd_conv_tc_plan_destroy", "rgbd_rb_plan_destroy", "rgbd_ssim_work_elems"])
 EXPORTS.remove("rgbd_conv_validate")
 
 _lib = None
@@ -131,6 +136,8 @@ def load():
     lib.rgbd_count_launch.argtypes = [C.c_int]
     lib.rgbd_conv_tc_plan_destroy.restype = None
     lib.rgbd_conv_tc_plan_destroy.argtypes = [_vp]
+    lib.rgbd_ssim_work_elems.restype = C.c_int64
+    lib.rgbd_ssim_work_elems.argtypes = [_i32, _i32, _i32]
     lib.rgbd_rb_plan_destroy.restype = None
     lib.rgbd_rb_plan_destroy.argtypes = [_vp]
     _lib = lib

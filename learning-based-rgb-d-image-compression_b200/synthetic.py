@@ -80,9 +80,10 @@ def synthetic_state_dict(model, seed=0, preset="mid"):
             v = t.clone()
         out[key] = v.to(t.dtype)
     # calibration: latent gain on the last analysis conv, log-uniform scale bias on every EP head
-    for br in ("rgb", "depth"):
-        for leaf in ("weight", "bias"):
-            k = f"g_a.{br}_analysis_transform.16.{leaf}"
+    # (united: index 16 of each branch; single-modality ELIC: index 13 of its one Sequential)
+    for k in [f"g_a.{br}_analysis_transform.16.{leaf}" for br in ("rgb", "depth") for leaf in ("weight", "bias")] + \
+            [f"g_a.analysis_transform.13.{leaf}" for leaf in ("weight", "bias")]:
+        if k in out:
             out[k] = out[k] * gain
     for key in list(out):
         if "entropy_parameters" in key and key.endswith("fusion.4.bias"):
