@@ -156,6 +156,14 @@ void rgbd_rb_plan_destroy(rgbd_rb_plan *p);
 int rgbd_se_scale(const void *x, int32_t dtype, int32_t N, int32_t HW, int32_t C, int32_t cstride,
                   int32_t coff, const float *w1, const float *w2, int32_t Cr, int32_t plus_one,
                   float *partial, int32_t nchunk, float *scale, void *stream);
+/* The same in two halves, for callers that keep the table of partial sums between calls and refresh only the channels
+ * that were rewritten (the Bi-CEE context buffer: the hyper-prior channels stay fixed over the 20 stages of
+ * models/elic_united.py:265-348).  partial[n][chunk][pstride]: rgbd_se_partial fills the channels [c0, c1) of the view;
+ * rgbd_se_gate turns the first C channels into scale[n][c]; work = N * (C + Cr) floats.  Bit-identical to rgbd_se_scale. */
+int rgbd_se_partial(const void *x, int32_t dtype, int32_t N, int32_t HW, int32_t cstride, int32_t coff, int32_t c0,
+                    int32_t c1, int32_t nchunk, float *partial, int32_t pstride, void *stream);
+int rgbd_se_gate(const float *partial, int32_t pstride, int32_t nchunk, int32_t N, int32_t HW, int32_t C,
+                 const float *w1, const float *w2, int32_t Cr, int32_t plus_one, float *work, float *scale, void *stream);
 /* y = x * scale[n, c]: applies the SE gate as a separate pass for the tensor-core conv path,
  * whose A operand goes HBM -> smem by TMA without passing through registers. */
 int rgbd_scale_channels(const void *x, void *y, int32_t dtype, const float *scale, int32_t N, int64_t HW,

@@ -6,19 +6,20 @@
 
 namespace {
 
-// partial[n][chunk][c] = sum over the chunk's pixels, fixed order
+// partial[n][chunk][c] = sum over the chunk's pixels, fixed order; channels [c0, c1) of the view, rows of the partial
+// table `pstride` floats apart (a caller that keeps the table can refresh only the channels that changed)
 template <typename T>
-__global__ void se_partial_kernel(const T *__restrict__ x, int HW, int C, int cstride, int coff,
-                                  int nchunk, float *__restrict__ partial) {
+__global__ void se_partial_kernel(const T *__restrict__ x, int HW, int c0, int c1, int cstride, int coff,
+                                  int nchunk, float *__restrict__ partial, int pstride) {
     const int n = blockIdx.x / nchunk, chunk = blockIdx.x % nchunk;
     const int per = (HW + nchunk - 1) / nchunk;
     const int p0 = chunk * per;
     const int p1 = min(HW, p0 + per);
-    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < C; c += gridDim.y * blockDim.x) {
+    for (int c = c0 + blockIdx.y * blockDim.x + threadIdx.x; c < c1; c += gridDim.y * blockDim.x) {
         const T *px = x + ((int64_t)n * HW + p0) * cstride + coff + c;
         float s = 0.f;
         for (int p = p0; p < p1; ++p, px += cstride) s += ElemIO<T>::ld(px);
-        partial[((int64_t)n * nchunk + chunk) * C + c] = s;
+        partial[((int64_t)n * nchunk + chunk) * pstride + c] = s;
     }
 }
 
@@ -26,13 +27,13 @@ __global__ void se_partial_kernel(const T *__restrict__ x, int HW, int C, int cs
 //   se_mean_kernel   : mean[n][c]   = (sum of the partials in fixed order) / HW
 //   se_hidden_kernel : hid[n][r]    = relu(W1[r,:] . mean[n,:])          one warp per (n, r)
 //   se_gate_kernel   : scale[n][c]  = sigmoid(W2[c,:] . hid[n,:]) (+1)   one warp per (n, c)
-__global__ void se_mean_kernel(const float *__restrict__ partial, int nchunk, int HW, int N, int C,
+__global__ void se_mean_kernel(const float *__restrict__ partial, int pstride, int nchunk, int HW, int N, int C,
                                float *__restrict__ mean) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (int64_t)N * C) return;
     const int n = (int)(e / C), c = (int)(e % C);
     float s = 0.f;
-    for (int k = 0; k < nchunk; ++k) s += partial[((int64_t)n * nchunk + k) * C + c];
+    for (int k = 0; k < nchunk; ++k) s += partial[((int64_t)n * nchunk + k) * pstride + c];
     mean[e] = s / (float)HW;
 }
 
@@ -267,30 +268,52 @@ extern "C" int rgbd_zero(void *p, int64_t bytes, void *stream) {
     return RGBD_OK;
 }
 
-extern "C" int rgbd_se_scale(const void *x, int32_t dtype, int32_t N, int32_t HW, int32_t C, int32_t cstride,
-                             int32_t coff, const float *w1, const float *w2, int32_t Cr, int32_t plus_one,
-                             float *partial, int32_t nchunk, float *scale, void *stream) {
-    RGBD_CHECK_ARG(x && w1 && w2 && partial && scale, "null pointer");
-    RGBD_CHECK_ARG(N > 0 && HW > 0 && C > 0 && Cr > 0 && nchunk > 0, "dims");
-
+// SE_Block in two halves so that a caller can keep the table of partial sums across calls and refresh only the channels
+// that were rewritten (the context buffer of the Bi-CEE chain: 1280 hyper-prior channels stay fixed over all 20 stages):
+//   rgbd_se_partial : partial[n][chunk][c] for the channels [c0, c1) of the view
+//   rgbd_se_gate    : scale[n][c] = sigmoid(W2 relu(W1 mean)) (+ 1) over the first C channels of the table
+// The sums are per channel and in a fixed order, so refreshing a sub-range gives the same bits as recomputing everything.
+extern "C" int rgbd_se_partial(const void *x, int32_t dtype, int32_t N, int32_t HW, int32_t cstride, int32_t coff,
+                               int32_t c0, int32_t c1, int32_t nchunk, float *partial, int32_t pstride, void *stream) {
+    RGBD_CHECK_ARG(x && partial, "null pointer");
+    RGBD_CHECK_ARG(N > 0 && HW > 0 && nchunk > 0 && 0 <= c0 && c0 < c1 && c1 <= pstride, "dims");
+    dim3 grid((unsigned)(N * nchunk), (unsigned)((c1 - c0 + 127) / 128));
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)(N * nchunk), (unsigned)((C + 127) / 128));
     if (dtype == RGBD_DT_F32)
-        se_partial_kernel<float><<<grid, 128, 0, st>>>((const float *)x, HW, C, cstride, coff, nchunk, partial);
+        se_partial_kernel<float><<<grid, 128, 0, st>>>((const float *)x, HW, c0, c1, cstride, coff, nchunk, partial, pstride);
     else
-        se_partial_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16 *)x, HW, C, cstride, coff,
-                                                                nchunk, partial);
+        se_partial_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16 *)x, HW, c0, c1, cstride, coff, nchunk,
+                                                                partial, pstride);
     RGBD_LAUNCH_CHECK();
-    // work buffers behind the partial sums: mean [N][C], hidden [N][Cr]
-    float *mean = partial + (int64_t)N * nchunk * C;
+    return RGBD_OK;
+}
+
+// work: N * (C + Cr) floats (mean, hidden)
+extern "C" int rgbd_se_gate(const float *partial, int32_t pstride, int32_t nchunk, int32_t N, int32_t HW, int32_t C,
+                            const float *w1, const float *w2, int32_t Cr, int32_t plus_one, float *work, float *scale,
+                            void *stream) {
+    RGBD_CHECK_ARG(partial && w1 && w2 && work && scale, "null pointer");
+    RGBD_CHECK_ARG(N > 0 && HW > 0 && C > 0 && Cr > 0 && nchunk > 0 && C <= pstride, "dims");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *mean = work;
     float *hid = mean + (int64_t)N * C;
-    se_mean_kernel<<<(unsigned)(((int64_t)N * C + 255) / 256), 256, 0, st>>>(partial, nchunk, HW, N, C, mean);
+    se_mean_kernel<<<(unsigned)(((int64_t)N * C + 255) / 256), 256, 0, st>>>(partial, pstride, nchunk, HW, N, C, mean);
     RGBD_LAUNCH_CHECK();
     se_hidden_kernel<<<(unsigned)(((int64_t)N * Cr * 32 + 255) / 256), 256, 0, st>>>(mean, w1, N, C, Cr, hid);
     RGBD_LAUNCH_CHECK();
     se_gate_kernel<<<(unsigned)(((int64_t)N * C * 32 + 255) / 256), 256, 0, st>>>(hid, w2, N, C, Cr, plus_one, scale);
     RGBD_LAUNCH_CHECK();
     return RGBD_OK;
+}
+
+extern "C" int rgbd_se_scale(const void *x, int32_t dtype, int32_t N, int32_t HW, int32_t C, int32_t cstride,
+                             int32_t coff, const float *w1, const float *w2, int32_t Cr, int32_t plus_one,
+                             float *partial, int32_t nchunk, float *scale, void *stream) {
+    RGBD_CHECK_ARG(C > 0, "dims");
+    int rc = rgbd_se_partial(x, dtype, N, HW, cstride, coff, 0, C, nchunk, partial, C, stream);
+    if (rc) return rc;
+    // work buffers behind the partial sums: mean [N][C], hidden [N][Cr]
+    return rgbd_se_gate(partial, C, nchunk, N, HW, C, w1, w2, Cr, plus_one, partial + (int64_t)N * nchunk * C, scale, stream);
 }
 
 extern "C" int rgbd_maxpool7s3(const void *x, void *y, int32_t dtype, int32_t N, int32_t H, int32_t W, int32_t C,

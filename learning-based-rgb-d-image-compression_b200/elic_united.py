@@ -492,6 +492,11 @@ class ELIC_united(nn.Module):
         M, gm = self.M, max(self.slice_ch)
         ctx = b.alloc(B, h, w, 4 * M + 8 * gm)
         ctx_rgb = None if self.cross else b.alloc(B, h, w, 2 * M + 4 * gm)
+        # the SE gates of the 20 EntropyParametersEX stages read growing prefixes of these buffers: keep the per-channel
+        # sums and refresh only what a stage's producers rewrote (the 2M / 4M hyper-prior channels never change)
+        b.se_cache(ctx)
+        if ctx_rgb is not None:
+            b.se_cache(ctx_rgb)
         return ctx, ctx_rgb
 
     # ------------------------------------------------------------------ programs
@@ -721,7 +726,8 @@ class ELIC_united(nn.Module):
         out_d = b.raw((B, 1, H, W), torch.float32)
         b.op("rgbd_nhwc_to_nchw", x_r.ptr(), _DT[x_r.dtype], out_r.data_ptr(), B, 3, H, W, x_r.cstride, x_r.coff, 1)
         b.op("rgbd_nhwc_to_nchw", x_d.ptr(), _DT[x_d.dtype], out_d.data_ptr(), B, 1, H, W, x_d.cstride, x_d.coff, 1)
-        p.io.update(st=st, out_r=out_r, out_d=out_d, yhat=yhat, ny=ny, nz=nz)
+        # (x_nhwc: the synthesis transform's output before the [0, 1] clamp of decompress(), for the parity tests)
+        p.io.update(st=st, out_r=out_r, out_d=out_d, yhat=yhat, ny=ny, nz=nz, x_nhwc={"r": x_r, "d": x_d})
         return p
 
     def _build_forward(self, B, H, W):

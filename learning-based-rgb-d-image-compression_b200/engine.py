@@ -238,6 +238,45 @@ class Program:
         self.graph = g
 
 
+def _subtract(ranges, lo, hi):
+    out = []
+    for a, b in ranges:
+        if b <= lo or a >= hi:
+            out.append((a, b))
+        else:
+            if a < lo:
+                out.append((a, lo))
+            if b > hi:
+                out.append((hi, b))
+    return out
+
+
+def _union(ranges, lo, hi):
+    keep = []
+    for a, b in ranges:
+        if b < lo or a > hi:
+            keep.append((a, b))
+        else:
+            lo, hi = min(lo, a), max(hi, b)
+    return sorted(keep + [(lo, hi)])
+
+
+def _missing(ranges, lo, hi):
+    """Sub-ranges of [lo, hi) not covered by the sorted disjoint `ranges`."""
+    out, p = [], lo
+    for a, b in ranges:
+        if b <= p:
+            continue
+        if a >= hi:
+            break
+        if a > p:
+            out.append((p, a))
+        p = max(p, b)
+    if p < hi:
+        out.append((p, hi))
+    return out
+
+
 class Builder:
     def __init__(self, device, act_dtype, tensor_cores=None):
         self.device = device
@@ -246,6 +285,7 @@ class Builder:
         self._wscratch = None   # per-image SE-folded filters of the layer being run (shared by all layers)
         self._sched = None      # tile counters of the persistent conv kernels (one int32 per plan, zero between launches)
         self._sched_used = 0
+        self._se_caches = {}    # id(buffer) -> table of SE partial sums kept across se_scale() calls
         self.stage = ""         # label of the part of the codec being compiled (g_a, h_a, h_s, chain, coder, g_s, io)
         # tcgen05 path: bf16 activations only
         self.tensor_cores = (act_dtype == torch.bfloat16) if tensor_cores is None else tensor_cores
@@ -444,6 +484,9 @@ class Builder:
                          + (opix * pc.Cout * esz if mul is not None else 0)
                          + len(ln["taps"]) * pc.Cin * pc.Cout * 2)
         self.prog.keep.extend([pc, x.buf, out.buf])
+        self._wrote(out)
+        if y2 is not None:
+            self._wrote(y2)
         if scaled is not None:
             self.release(scaled)
         return out
@@ -487,19 +530,48 @@ class Builder:
         self.prog.flops += run.flops
         run.bytes = px * (x.C + 2 * pc3.Cout) * 2 + (x.C * 96 + 9 * 96 * 96 + 96 * pc3.Cout) * 2
         self.prog.keep.extend([d, pc1, pc2, pc3, w1, w2, w3, x.buf, res.buf, out.buf])
+        self._wrote(out)
         return out
 
     def se_scale(self, x, w1, w2, plus_one):
-        """SE_Block channel gate of `x` -> fp32 [N, C] scale tensor."""
+        """SE_Block channel gate of `x` -> fp32 [N, C] scale tensor.  For a buffer registered with se_cache() the table of
+        per-channel partial sums persists between calls and only channels written since (tracked by conv / fused_block)
+        are summed again — the same bits as a full recomputation, the sums being per channel and in a fixed order."""
         Cr = w1.shape[0]
         HW = x.H * x.W
         nchunk = max(1, min(64, HW // 64))
-        partial = self.raw((x.N * (nchunk * x.C + x.C + Cr),), torch.float32)
         scale = self.raw((x.N, x.C), torch.float32)
-        self.op("rgbd_se_scale", x.ptr(), _DT[x.dtype], x.N, HW, x.C, x.cstride, x.coff, w1.data_ptr(),
-                w2.data_ptr(), Cr, int(plus_one), partial.data_ptr(), nchunk, scale.data_ptr())
+        cache = self._se_caches.get(id(x.buf))
         self.prog.keep.extend([w1, w2])
+        if cache is None:
+            partial = self.raw((x.N * (nchunk * x.C + x.C + Cr),), torch.float32)
+            self.op("rgbd_se_scale", x.ptr(), _DT[x.dtype], x.N, HW, x.C, x.cstride, x.coff, w1.data_ptr(),
+                    w2.data_ptr(), Cr, int(plus_one), partial.data_ptr(), nchunk, scale.data_ptr())
+            return scale
+        assert x.coff == 0, "cached SE sums are indexed by the buffer's own channels"
+        pstride = x.cstride
+        if "partial" not in cache:
+            cache["partial"] = self.raw((x.N * nchunk * pstride,), torch.float32)
+            cache["work"] = self.raw((x.N * (pstride + 4096),), torch.float32)
+            cache["valid"] = []            # disjoint sorted [lo, hi) channel ranges whose sums are current
+        assert Cr <= 4096
+        for lo, hi in _missing(cache["valid"], 0, x.C):
+            self.op("rgbd_se_partial", x.ptr(), _DT[x.dtype], x.N, HW, x.cstride, 0, lo, hi, nchunk,
+                    cache["partial"].data_ptr(), pstride)
+        cache["valid"] = _union(cache["valid"], 0, x.C)
+        self.op("rgbd_se_gate", cache["partial"].data_ptr(), pstride, nchunk, x.N, HW, x.C, w1.data_ptr(), w2.data_ptr(),
+                Cr, int(plus_one), cache["work"].data_ptr(), scale.data_ptr())
         return scale
+
+    def se_cache(self, view):
+        """Keep the SE partial sums of this buffer between se_scale() calls (see there)."""
+        self._se_caches.setdefault(id(view.buf), {})
+
+    def _wrote(self, view):
+        """A launch writes channels [coff, coff + C) of view.buf: their cached SE sums are stale."""
+        cache = self._se_caches.get(id(view.buf))
+        if cache and "valid" in cache:
+            cache["valid"] = _subtract(cache["valid"], view.coff, view.coff + view.C)
 
     def maxpool7s3(self, x):
         assert x.coff == 0 and x.C == x.cstride

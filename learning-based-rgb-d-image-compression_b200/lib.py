@@ -74,6 +74,8 @@ _PROTOS = {
     "rgbd_rb_plan_create": [C.POINTER(RbDesc), C.POINTER(_vp)],
     "rgbd_rb_run": [_vp, _vp],
     "rgbd_se_scale": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp],
+    "rgbd_se_partial": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+    "rgbd_se_gate": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp],
     "rgbd_maxpool7s3": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_nchw_to_nhwc": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_nhwc_to_nchw": [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],

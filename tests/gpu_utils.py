@@ -72,3 +72,36 @@ def make_model(cls=None, preset="mid", seed=0, precision="fp32", **kw):
 def psnr(a, b):
     mse = float(((a.double() - b.double()) ** 2).mean())
     return 99.0 if mse == 0 else 10 * np.log10(1.0 / mse)
+
+
+def nchw(view):
+    """NHWC channel view of a launch plan -> fp32 NCHW tensor on the CPU."""
+    return view.torch().float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def recon_fidelity_db(x_gpu, x_ref):
+    """Distance between a GPU reconstruction and the oracle's synthesis transform run ON THE SAME y_hat, as a PSNR whose
+    peak is 4 x the standard deviation of the oracle's output (the peak-to-sigma ratio of a natural image in [0, 1]).
+    Why not PSNR(x_hat_gpu, x_hat_oracle) of two complete codecs: their y_hat differ wherever a bf16 rounding flips a
+    quantised symbol (a few % of sites, by one step), and the random-init synthesis transform amplifies every flip to
+    O(1) pixel differences (its outputs are not images: |x_hat| reaches 50), so that figure measures the chaos of the
+    stand-in weights, not the accuracy of the kernels.  With y_hat held fixed the figure isolates g_s."""
+    x_gpu, x_ref = x_gpu.double().cpu(), x_ref.double().cpu()
+    mse = float(((x_gpu - x_ref) ** 2).mean())
+    peak2 = 16.0 * float(x_ref.var())
+    return 99.0 if mse == 0 else 10 * np.log10(peak2 / mse)
+
+
+# bf16 mode: the reconstruction may sit at most this far below what bf16 arithmetic itself costs (oracle/bf16_emulation.py:
+# 40 - 45 dB on the synthetic weights), and never below the absolute floor
+FIDELITY_MARGIN_DB = 1.5
+FIDELITY_FLOOR_DB = 38.0
+
+
+def check_recon_fidelity(tag, x_gpu, gs_fp32, gs_bf16_emulated):
+    """x_gpu against the fp32 oracle's g_s on the same y_hat, held to the bf16 emulation's distance from that oracle."""
+    got = recon_fidelity_db(x_gpu, gs_fp32)
+    emu = recon_fidelity_db(gs_bf16_emulated, gs_fp32)
+    assert got >= emu - FIDELITY_MARGIN_DB and got >= FIDELITY_FLOOR_DB, \
+        f"{tag}: reconstruction {got:.2f} dB from the fp32 oracle; bf16 arithmetic itself costs {emu:.2f} dB"
+    return got, emu

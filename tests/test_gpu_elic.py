@@ -81,11 +81,14 @@ def test_elic_bf16_batch_and_multistream(channel):
     assert rec["x_hat"].shape == (3, channel, 128, 128) and torch.isfinite(rec["x_hat"]).all()
     # rate and reconstruction close to the fp32 oracle
     ref_c = orc.compress(x[:1])
-    ref = orc.decompress(ref_c["strings"], ref_c["shape"])
     want = len(ref_c["strings"][0][0]) + len(ref_c["strings"][1][0])
     got = len(out["strings"][0][0]) + len(out["strings"][1][0])
     assert abs(got - want) <= 0.005 * want, (got, want)
-    assert float(((rec["x_hat"][:1].cpu() - ref["x_hat"]) ** 2).mean()) < 2e-3
+    # reconstruction: against the oracle's g_s on the GPU's own y_hat (gpu_utils.recon_fidelity_db says why)
+    from gpu_utils import check_recon_fidelity, nchw
+    from oracle.bf16_emulation import Bf16ElicOracle
+    yh = nchw(dec.io["yhat"])
+    check_recon_fidelity(f"ELIC channel {channel}", rec["x_hat"], orc.g_s1(yh), Bf16ElicOracle(orc.sd).g_s1(yh))
     # per-image bytes do not depend on the batch
     one = net.compress(x[1:2].to(DEV))
     assert one["strings"][0][0] == out["strings"][0][1] and one["strings"][1][0] == out["strings"][1][1]

@@ -101,14 +101,17 @@ def test_fused_block_is_deterministic_and_batch_invariant():
 
 def test_model_with_fused_blocks_matches_unfused_model():
     """The whole codec with fused bottleneck blocks: same symbols rate (within 0.5 %) as the unfused launch list, exact
-    round trip, and it really runs fewer launches."""
+    round trip, reconstruction as close to the oracle's g_s on the same y_hat as bf16 arithmetic allows, and it really
+    runs fewer launches."""
     import rgbd_b200
-    from gpu_utils import make_model
+    from gpu_utils import check_recon_fidelity, make_model, nchw
+    from oracle.bf16_emulation import Bf16OracleCodec
+    from oracle.model_oracle import OracleCodec
     from rgbd_b200.synthetic import synthetic_pairs
     rgb, depth = synthetic_pairs(2, 128, 192, seed=5)
     outs = {}
     for fuse in (True, False):
-        net, _ = make_model(rgbd_b200.ELIC_united, "mid", 0, precision="bf16", fuse_blocks=fuse)
+        net, sd = make_model(rgbd_b200.ELIC_united, "mid", 0, precision="bf16", fuse_blocks=fuse)
         c = net.compress(rgb.to(DEV), depth.to(DEV))
         enc = net._program("encoder", 2, 128, 192)
         sym = {k: enc.io["st"][k]["ysym"].clone() for k in ("r", "d")}
@@ -116,12 +119,13 @@ def test_model_with_fused_blocks_matches_unfused_model():
         dec = net._program("decoder", 2, 2, 3)
         for k in ("r", "d"):
             assert torch.equal(dec.io["st"][k]["ysym"], sym[k]), (fuse, k)
+        yh = [nchw(dec.io["yhat"][k]) for k in ("r", "d")]
+        gs, gs_emu = (dict(zip(("r", "d"), o.g_s(*yh))) for o in (OracleCodec(sd), Bf16OracleCodec(sd)))
+        for k in ("r", "d"):
+            check_recon_fidelity(f"fused={fuse} {k}", nchw(dec.io["x_nhwc"][k]), gs[k], gs_emu[k])
         outs[fuse] = (c, r, len(enc.ops) + len(dec.ops), len(enc.rb_plans) + len(dec.rb_plans))
     assert outs[True][3] > 0 and outs[False][3] == 0 and outs[True][2] < outs[False][2]
     for key in ("r_strings", "d_strings"):
         a = sum(len(s) for g in outs[True][0][key] for s in g)
         b = sum(len(s) for g in outs[False][0][key] for s in g)
         assert abs(a - b) <= 0.005 * b, (key, a, b)
-    for m in ("r", "d"):
-        mse = float(((outs[True][1]["x_hat"][m] - outs[False][1]["x_hat"][m]) ** 2).mean())
-        assert mse < 1e-3, (m, mse)

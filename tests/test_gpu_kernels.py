@@ -228,6 +228,40 @@ def test_se_maxpool_layout():
     assert torch.equal(back.cpu(), img.clamp(0, 1))
 
 
+def test_se_cached_table_equals_full_recomputation():
+    """se_scale on a buffer registered with Builder.se_cache: growing prefixes, channel ranges rewritten by convs in
+    between — every gate is bit-identical to the uncached kernel run on the same buffer contents."""
+    import torch.nn as nn
+    from rgbd_b200.engine import Builder, PackedConv, View
+    torch.manual_seed(14)
+    dev = torch.device(DEV)
+    outs = {}
+    for cached in (True, False):
+        torch.manual_seed(15)
+        b = Builder(dev, torch.float32, tensor_cores=False)
+        buf = b.alloc(2, 12, 20, 96)
+        buf.buf.copy_(torch.randn(2, 12, 20, 96))
+        src = b.alloc(2, 12, 20, 8)
+        src.buf.copy_(torch.randn(2, 12, 20, 8))
+        if cached:
+            b.se_cache(buf)
+        convs = [PackedConv(nn.Conv2d(8, 16, 3, 1, 1), dev) for _ in range(3)]
+        gates = []
+        for width, (pc, off) in zip((40, 64, 96, 96), [(None, 0), (convs[0], 24), (convs[1], 70), (convs[2], 0)]):
+            if pc is not None:
+                b.conv(pc, src, out=buf.sub(off, 16))          # rewrites 16 channels: their sums go stale
+            w1, w2 = (torch.randn(5, width) * 0.2).to(dev), (torch.randn(width, 5) * 0.2).to(dev)
+            gates.append(b.se_scale(buf.sub(0, width), w1, w2, plus_one=True))
+        b.prog.run()
+        torch.cuda.synchronize()
+        outs[cached] = [g.cpu() for g in gates]
+        if cached:
+            n_partial = sum(1 for op in b.prog.ops if getattr(op, "label", "") == "rgbd_se_partial")
+            assert n_partial == 4      # [0, 40) | [24, 64) | [64, 96) | [0, 16): one refresh per call, never the whole table
+    for a, c in zip(outs[False], outs[True]):
+        assert torch.equal(a, c)
+
+
 def test_likelihood_kernels_vs_torch():
     """forward()-only kernels: erfc / sigmoid chains, fp32 tolerance 1e-5 absolute."""
     import rgbd_b200

@@ -274,3 +274,28 @@ def test_cpu_arm_does_not_load_the_product_library():
     out = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.strip().splitlines()[-1] == "CLEAN True", out.stdout
+
+
+def test_se_cache_range_bookkeeping():
+    """engine._missing / _union / _subtract: which channels of the SE partial-sum table need refreshing."""
+    from rgbd_b200.engine import _missing, _subtract, _union
+    rng = random.Random(7)
+    for _ in range(200):
+        truth = [False] * 64
+        ranges = []
+        for _ in range(12):
+            lo = rng.randrange(0, 63)
+            hi = rng.randrange(lo + 1, 65)
+            if rng.random() < 0.5:
+                ranges = _union(ranges, lo, hi)
+                truth[lo:hi] = [True] * (hi - lo)
+            else:
+                ranges = _subtract(ranges, lo, hi)
+                truth[lo:hi] = [False] * (hi - lo)
+            assert all(a < b for a, b in ranges) and all(ranges[i][1] <= ranges[i + 1][0] for i in range(len(ranges) - 1))
+            got = [any(a <= c < b for a, b in ranges) for c in range(64)]
+            assert got == truth
+            qlo = rng.randrange(0, 63)
+            qhi = rng.randrange(qlo + 1, 65)
+            miss = _missing(ranges, qlo, qhi)
+            assert [any(a <= c < b for a, b in miss) for c in range(64)] == [qlo <= c < qhi and not truth[c] for c in range(64)]
