@@ -98,10 +98,11 @@ FIDELITY_MARGIN_DB = 1.5
 FIDELITY_FLOOR_DB = 38.0
 
 
-def check_recon_fidelity(tag, x_gpu, gs_fp32, gs_bf16_emulated):
-    """x_gpu against the fp32 oracle's g_s on the same y_hat, held to the bf16 emulation's distance from that oracle."""
+def check_recon_fidelity(tag, x_gpu, gs_fp32, gs_bf16_emulated, floor_db=FIDELITY_FLOOR_DB):
+    """x_gpu against the fp32 oracle's g_s on the same y_hat, held to the bf16 emulation's distance from that oracle
+    (floor_db = None for the `stress` weights, whose scales in the hundreds put bf16 itself at ~29 dB)."""
     got = recon_fidelity_db(x_gpu, gs_fp32)
     emu = recon_fidelity_db(gs_bf16_emulated, gs_fp32)
-    assert got >= emu - FIDELITY_MARGIN_DB and got >= FIDELITY_FLOOR_DB, \
+    assert got >= emu - FIDELITY_MARGIN_DB and (floor_db is None or got >= floor_db), \
         f"{tag}: reconstruction {got:.2f} dB from the fp32 oracle; bf16 arithmetic itself costs {emu:.2f} dB"
     return got, emu
