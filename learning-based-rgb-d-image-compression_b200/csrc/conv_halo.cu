@@ -427,14 +427,10 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                 const bool on = valid && c < nchunks && d.Cout - co >= 16;
                 pr[0] = pr[1] = pm[0] = pm[1] = make_uint4(0, 0, 0, 0);
                 if (on && res_direct && res_vec) {
-                    const uint4 *q = reinterpret_cast<const uint4 *>(res + opix * d.res_cstride + d.res_coff + co);
-                    pr[0] = q[0];
-                    pr[1] = q[1];
+                    ldg_2x128(res + opix * d.res_cstride + d.res_coff + co, pr[0], pr[1]);
                 }
                 if (kGate && on && mul_vec && !mul_staged) {
-                    const uint4 *q = reinterpret_cast<const uint4 *>(mul + opix * d.mul_cstride + d.mul_coff + co);
-                    pm[0] = q[0];
-                    pm[1] = q[1];
+                    ldg_2x128(mul + opix * d.mul_cstride + d.mul_coff + co, pm[0], pm[1]);
                 }
             };
             const int nblk = (nchunks + 1) >> 1;

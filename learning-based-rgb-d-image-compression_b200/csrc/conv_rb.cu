@@ -7,22 +7,29 @@
 // C/2-channel intermediates kept ON CHIP: unfused, a block moves 960 channel-units per pixel through HBM
 // (x, t1 out/in, t2 out/in, x again, y); fused it moves 384 + halo.
 //
-// One persistent CTA per SM walks output tiles of R rows x TW columns (positions laid out with row pitch P = TW + 2,
-// R * P <= 256 = two M tiles).  Per tile, three GEMM phases share the tensor pipe:
-//   P1  t1 = relu(W1 x + b1) on the tile PLUS its one-pixel halo ((R + 2) x P positions <= 384 = three M tiles).  The x halo
-//       tile streams through a 2-stage TMA ring one 64-channel block at a time; accumulators D1 live in TMEM columns [0, 288).
-//       The epilogue warps turn D1 into bf16 t1 in shared memory (two 128-byte-row planes: channels 0-63 and 64-95, written
-//       with the 128-byte swizzle a TMA load would have produced), forcing positions outside the image to ZERO — the 3x3
-//       conv of the reference pads t1 with zeros, not with relu(b1).
+// Geometry.  Positions are laid out with a power-of-two row pitch P (32 or 64), so one M tile of 128 positions is
+// rpm = 128 / P whole rows and position <-> (row, column) is a shift and a mask.  A tile produces 2 M tiles of output
+// (R = 2 rpm rows x TW = P - 2 useful columns); its one-pixel halo — (R + 2) rows x P columns starting one pixel up and
+// left — fits 3 M tiles.  One persistent CTA per SM walks the tiles.  Per tile, three GEMM phases share the tensor pipe:
+//   P1  t1 = relu(W1 x + b1) on the halo (3 M tiles, one after the other, so that the epilogue of a finished M tile runs
+//       under the MMAs of the next).  x arrives as 16 KB pieces {64 channels, P columns, rpm rows} = one (channel block, M
+//       tile) each, through a 4-deep TMA ring; the NEXT tile's pieces are prefetched into L2 while this
+//       tile computes (cp.async.bulk.prefetch.tensor), so the ring refills at L2 latency, not HBM latency.  Accumulators
+//       D1[m] in TMEM columns [0, 288).  The epilogue warps turn D1 into bf16 t1 in shared memory (two 128-byte-row planes:
+//       channels 0-63 and 64-95, written with the 128-byte swizzle a TMA load would have produced), forcing positions
+//       outside the image to ZERO — the 3x3 conv of the reference pads t1 with zeros, not with relu(b1).
 //   P2  t2 = relu(W2 (*) t1 + b2): implicit GEMM over the 9 taps; the A operand of tap (ky, kx) is the t1 plane read
 //       through a UMMA descriptor whose start address is shifted by ky * P + kx rows (the halo trick of conv_halo.cu).
-//       D2 in TMEM columns [288, 480).  t2 overwrites t1 in shared memory (every P2 MMA has completed by then).
-//   P3  y = act(W3 t2 + b3 + res): four 48-channel output blocks, double buffered in the D2 region so that the epilogue of
-//       one block (residual from global / L2, bf16 NHWC stores) overlaps the MMAs of the next, and P1 of the NEXT tile
-//       (D1 columns are free again) overlaps the last epilogue.
+//       D2[j] in TMEM columns [288, 480).  t2 overwrites t1 in shared memory (every P2 MMA has completed by then).
+//   P3  y = act(W3 t2 + b3 + res): four 48-channel output blocks per M tile, double buffered in the D2[j] region so that
+//       the epilogue of one block (residual from L2, bf16 NHWC stores) overlaps the MMAs of the next, and P1 of the NEXT
+//       tile (D1 columns are free again) overlaps the last epilogues.
 // Weights stream from L2 through a 4-stage ring of 12 KB planes [96 rows x 64 K]; the K tails (channels 64-95) of two
-// consecutive 3x3 taps share one plane (no zero padding is fetched).  Warp roles: 0 = x producer, 1 = weight producer,
-// 2 / 3 = MMA issuers (one accumulator M tile each; warp 2 also issues the third halo M tile and owns TMEM), 4-11 = epilogue.
+// consecutive 3x3 taps share one plane (no zero padding is fetched); a W3 stage holds both K planes of one output block.
+// Warp roles: 0 = x producer, 1 = weight producer, 2 / 3 = MMA issuers (output M tile j = warp - 2; halo M tiles 0 and 2
+// / 1; warp 2 owns TMEM), 4-11 = epilogue (TMEM lane quadrant = warp % 4; warps 4-7 serve M tile 0, warps 8-11 M tile 1,
+// both halves of the third halo tile).  Every hand-over is its own mbarrier (per halo M tile, per output M tile, per
+// output-block buffer), the epilogues run one TMEM load ahead of the arithmetic, and no integer division is left in them.
 // K order is fixed (channel blocks, taps, 16-channel steps), so results do not depend on batch size or tile position.
 #include "tc_common.cuh"
 #include <new>
@@ -31,13 +38,17 @@
 namespace {
 
 constexpr int kRbThreads = 384;
-constexpr int kXStages = 2, kWStages = 4;
+constexpr int kXStages = 4, kWStages = 4;
+constexpr int kXStageBytes = 128 * 128;       // 16 KB: one M tile of positions x 64 channels (bf16)
 constexpr int kCm = 96;                       // bottleneck width (C / 2)
 constexpr int kWStageBytes = kCm * 128;       // 12 KB: 96 rows x 64 K (bf16)
 constexpr int kNB3 = 48;                      // output-channel block of P3
+constexpr int kTRows = 384;                   // rows of a t plane = 3 M tiles
+constexpr int kTBytes = kTRows * 128;
 constexpr uint32_t kRbTmemCols = 512;
 constexpr int kD2Col = 3 * kCm;               // 288
 constexpr int kMaxCout = 192;
+constexpr int kRbBarriers = 2 * kXStages + 2 * kWStages + 3 + 3 + 2 + 2 + 4 + 4;
 
 struct RbParams {
     CUtensorMap xmap, w1map, w2map, w3map;
@@ -46,9 +57,9 @@ struct RbParams {
     __nv_bfloat16 *y;
     int32_t N, H, W, Cin, Cout;
     int32_t res_cstride, res_coff, y_cstride, y_coff;
-    int32_t TW, R, P, tiles_x, tiles_y, total_tiles;
-    int32_t kb1, nblk3, final_relu;
-    int32_t x_bytes, x_tx, t_rows, t_bytes;
+    int32_t TW, R, P, LP, rpm, tiles_x, tiles_y, total_tiles;
+    int32_t kb1, nblk3, final_relu, prefetch, wide_io;   // wide_io: res / y rows are 32-byte aligned
+    long long *dbg;   // optional cycle counters of CTA 0 (development builds: RGBD_TIMING_PROBES + RGBD_TC_TRACE), else NULL
 };
 
 struct RbTile {
@@ -59,12 +70,18 @@ __device__ __forceinline__ RbTile rb_tile(const RbParams &p, int tile) {
     const int per_img = p.tiles_x * p.tiles_y;
     t.n = tile / per_img;
     const int r = tile - t.n * per_img;
-    t.oy0 = (r / p.tiles_x) * p.R;
-    t.ox0 = (r % p.tiles_x) * p.TW;
+    const int tyi = r / p.tiles_x;
+    t.oy0 = tyi * p.R;
+    t.ox0 = (r - tyi * p.tiles_x) * p.TW;
     return t;
 }
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2),
+                 "r"(c3)
+                 : "memory");
+}
 
 __global__ void __launch_bounds__(kRbThreads, 1)
 rb_fused_kernel(const __grid_constant__ RbParams p) {
@@ -73,18 +90,21 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const uint32_t x_base = base;
-    const uint32_t t_base = x_base + (uint32_t)(kXStages * p.x_bytes);          // plane 0, then plane 1
-    const uint32_t w_base = t_base + 2u * (uint32_t)p.t_bytes;
+    const uint32_t t_base = x_base + (uint32_t)(kXStages * kXStageBytes);          // plane 0, then plane 1
+    const uint32_t w_base = t_base + 2u * (uint32_t)kTBytes;
     const uint32_t bar_base = w_base + (uint32_t)(kWStages * kWStageBytes);
     auto x_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
     auto x_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kXStages + s); };
     auto w_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kXStages + s); };
     auto w_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kXStages + kWStages + s); };
     const uint32_t misc = bar_base + 8u * (uint32_t)(2 * kXStages + 2 * kWStages);
-    const uint32_t d1_full = misc, t1_ready = misc + 8, d2_full = misc + 16, t2_ready = misc + 24;
-    auto d3_full = [&](int b) { return misc + 32u + 8u * (uint32_t)b; };
-    auto d3_empty = [&](int b) { return misc + 48u + 8u * (uint32_t)b; };
-    const uint32_t tmem_slot = misc + 64;
+    auto d1_full = [&](int m) { return misc + 8u * (uint32_t)m; };                  // P1 MMAs of halo M tile m complete
+    auto t1_ready = [&](int m) { return misc + 24u + 8u * (uint32_t)m; };           // t1 rows of halo M tile m are in shared memory
+    auto d2_full = [&](int j) { return misc + 48u + 8u * (uint32_t)j; };
+    auto t2_ready = [&](int j) { return misc + 64u + 8u * (uint32_t)j; };
+    auto d3_full = [&](int j, int b) { return misc + 80u + 8u * (uint32_t)(2 * j + b); };
+    auto d3_empty = [&](int j, int b) { return misc + 112u + 8u * (uint32_t)(2 * j + b); };
+    const uint32_t tmem_slot = misc + 144u;
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
     float *bias_s = reinterpret_cast<float *>(smem_raw + (tmem_slot + 16u - raw));   // b1[96] | b2[96] | b3[Cout]
 
@@ -92,19 +112,23 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kXStages; ++s) {
             mbar_init(x_full(s), 1);
-            mbar_init(x_empty(s), 2);
+            mbar_init(x_empty(s), 2);      // a piece feeds one issuer warp, but BOTH pass every stage (see the P1 loop)
         }
         for (int s = 0; s < kWStages; ++s) {
             mbar_init(w_full(s), 1);
-            mbar_init(w_empty(s), 2);
+            mbar_init(w_empty(s), 2);      // every weight stage feeds both issuer warps
         }
-        mbar_init(d1_full, 2);
-        mbar_init(t1_ready, 8);
-        mbar_init(d2_full, 2);
-        mbar_init(t2_ready, 8);
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(d3_full(b), 2);
-            mbar_init(d3_empty(b), 8);
+        for (int m = 0; m < 3; ++m) {
+            mbar_init(d1_full(m), 1);
+            mbar_init(t1_ready(m), m < 2 ? 4 : 8);
+        }
+        for (int j = 0; j < 2; ++j) {
+            mbar_init(d2_full(j), 1);
+            mbar_init(t2_ready(j), 4);
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(d3_full(j, b), 1);
+                mbar_init(d3_empty(j, b), 4);
+            }
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -123,90 +147,127 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
     const int first = (int)blockIdx.x, step = (int)gridDim.x;
 
     if (warp == 0) {
-        // =========================== x producer: halo tile, one 64-channel block per stage ===========================
+        // =========================== x producer: one (channel block, halo M tile) piece per stage ===========================
         if (lane == 0) {
             RingPos rx = {0, 0};
+            const bool tr = p.dbg != nullptr && blockIdx.x == 0;
+            long long wx = 0;
             griddep_wait();
             for (int tile = first; tile < p.total_tiles; tile += step) {
                 const RbTile tc = rb_tile(p, tile);
-                for (int kb = 0; kb < p.kb1; ++kb, rx.next(kXStages)) {
-                    mbar_wait(x_empty(rx.s), rx.ph ^ 1u);
-                    mbar_expect_tx(x_full(rx.s), (uint32_t)p.x_tx);
-                    tma_load_4d(x_base + (uint32_t)(rx.s * p.x_bytes), &p.xmap, x_full(rx.s), kb * kBlockK, tc.ox0 - 1, tc.oy0 - 1,
-                                tc.n);
+                if (p.prefetch && tile + step < p.total_tiles) {
+                    // the next tile's pieces start their way HBM -> L2 now: the ring can hold only 4 of its 9+ pieces ahead of time
+                    const RbTile tn = rb_tile(p, tile + step);
+                    for (int m = 0; m < 3; ++m)
+                        for (int kb = 0; kb < p.kb1; ++kb) tma_prefetch_4d(&p.xmap, kb * kBlockK, tn.ox0 - 1, tn.oy0 - 1 + m * p.rpm, tn.n);
+                }
+                // halo M tile by halo M tile (all channel blocks of tile 0, then of tile 1, ...): D1[0] completes a third of the
+                // way into P1, so its epilogue runs under the MMAs of the other two
+                for (int m = 0; m < 3; ++m) {
+                    for (int kb = 0; kb < p.kb1; ++kb, rx.next(kXStages)) {
+                        mbar_wait_t(x_empty(rx.s), rx.ph ^ 1u, tr, wx);
+                        mbar_expect_tx(x_full(rx.s), (uint32_t)kXStageBytes);
+                        tma_load_4d(x_base + (uint32_t)(rx.s * kXStageBytes), &p.xmap, x_full(rx.s), kb * kBlockK, tc.ox0 - 1,
+                                    tc.oy0 - 1 + m * p.rpm, tc.n);
+                    }
                 }
             }
             griddep_launch();
+            if (tr) p.dbg[0] = wx;
         }
     } else if (warp == 1) {
         // =========================== weight producer ===========================
         if (lane == 0) {
             RingPos rw = {0, 0};
-            auto load = [&](const CUtensorMap *map, uint32_t bytes, int c0, int c1, int c2) {
-                mbar_wait(w_empty(rw.s), rw.ph ^ 1u);
-                mbar_expect_tx(w_full(rw.s), bytes);
-                tma_load_3d(w_base + (uint32_t)(rw.s * kWStageBytes), map, w_full(rw.s), c0, c1, c2);
-                rw.next(kWStages);
-            };
+            const bool tr = p.dbg != nullptr && blockIdx.x == 0;
+            long long ww = 0;
             for (int tile = first; tile < p.total_tiles; tile += step) {
-                for (int kb = 0; kb < p.kb1; ++kb) load(&p.w1map, kWStageBytes, kb * kBlockK, 0, 0);
-                for (int s = 0; s < 14; ++s) load(&p.w2map, kWStageBytes, 0, 0, s);
-                for (int blk = 0; blk < p.nblk3; ++blk)
-                    for (int pl = 0; pl < 2; ++pl) load(&p.w3map, kNB3 * 128, pl * kBlockK, blk * kNB3, 0);
+                for (int mk = 0; mk < 3 * p.kb1; ++mk, rw.next(kWStages)) {      // W1 once per halo M tile (P1 runs M tile by M tile)
+                    mbar_wait_t(w_empty(rw.s), rw.ph ^ 1u, tr, ww);
+                    mbar_expect_tx(w_full(rw.s), (uint32_t)kWStageBytes);
+                    tma_load_3d(w_base + (uint32_t)(rw.s * kWStageBytes), &p.w1map, w_full(rw.s), (mk % p.kb1) * kBlockK, 0, 0);
+                }
+                for (int s = 0; s < 14; ++s, rw.next(kWStages)) {
+                    mbar_wait_t(w_empty(rw.s), rw.ph ^ 1u, tr, ww);
+                    mbar_expect_tx(w_full(rw.s), (uint32_t)kWStageBytes);
+                    tma_load_3d(w_base + (uint32_t)(rw.s * kWStageBytes), &p.w2map, w_full(rw.s), 0, 0, s);
+                }
+                for (int blk = 0; blk < p.nblk3; ++blk, rw.next(kWStages)) {
+                    // both K planes of one 48-channel output block in one stage: [48 rows x K 0-63] then [48 rows x K 64-127]
+                    mbar_wait_t(w_empty(rw.s), rw.ph ^ 1u, tr, ww);
+                    mbar_expect_tx(w_full(rw.s), (uint32_t)(2 * kNB3 * 128));
+                    const uint32_t dst = w_base + (uint32_t)(rw.s * kWStageBytes);
+                    tma_load_3d(dst, &p.w3map, w_full(rw.s), 0, blk * kNB3, 0);
+                    tma_load_3d(dst + (uint32_t)(kNB3 * 128), &p.w3map, w_full(rw.s), kBlockK, blk * kNB3, 0);
+                }
             }
+            if (tr) p.dbg[1] = ww;
         }
     } else if (warp == 2 || warp == 3) {
         // =========================== MMA issuers ===========================
-        const int wi = warp - 2;                 // accumulator M tile of P2 / P3; P1: warp 2 -> halo M tiles 0 and 2, warp 3 -> 1
+        const int wi = warp - 2;                 // output M tile of P2 / P3; P1: warp 2 -> halo M tiles 0 and 2, warp 3 -> 1
         const uint64_t desc0 = make_smem_desc(0);
         const uint32_t idesc96 = make_idesc(128, kCm), idesc48 = make_idesc(128, kNB3);
-        const uint32_t xb = x_base >> 4, wb = w_base >> 4, t0b = t_base >> 4, t1b = (t_base + (uint32_t)p.t_bytes) >> 4;
+        const uint32_t xb = x_base >> 4, wb = w_base >> 4, t0b = t_base >> 4, t1b = (t_base + (uint32_t)kTBytes) >> 4;
         const uint32_t mrow = (128u * 128u) >> 4;                    // one M tile of rows in descriptor units
         RingPos rx = {0, 0}, rw = {0, 0};
         uint32_t it = 0;
+        const bool tr = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+        long long m_w1 = 0, m_x = 0, m_pre2 = 0, m_w2 = 0, m_t2 = 0, m_e3 = 0, m_w3 = 0;
+        const long long m_begin = tr ? clock64() : 0;
         for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
-            // ---------------- P1 ----------------
-            for (int kb = 0; kb < p.kb1; ++kb) {
-                mbar_wait(x_full(rx.s), rx.ph);
-                mbar_wait(w_full(rw.s), rw.ph);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t a_lo = xb + (uint32_t)((rx.s * p.x_bytes) >> 4), b_lo = wb + (uint32_t)((rw.s * kWStageBytes) >> 4);
-                    for (int m = wi; m < 3; m += 2) {
-                        const uint32_t dcol = tmem_base + (uint32_t)(m * kCm);
-                        issue_mmas(dcol, desc0 + (uint64_t)(a_lo + (uint32_t)m * mrow), desc0 + (uint64_t)b_lo, idesc96, kb > 0 ? 1u : 0u, 4);
+            // ---------------- P1 (D1[m] was drained by the epilogue of the previous tile: t1_ready waits below) ----------------
+            for (int m = 0; m < 3; ++m) {
+                const bool mine = (m == 1) == (wi == 1);
+                for (int kb = 0; kb < p.kb1; ++kb, rx.next(kXStages), rw.next(kWStages)) {
+                    // Both issuer warps wait for and release EVERY stage, also those whose MMAs the other warp issues: a
+                    // parity wait is only meaningful for a waiter that has seen the previous phase of the same barrier, so
+                    // nobody may skip a stage (and the producers must not run more than one ring round ahead of either warp).
+                    mbar_wait_t(w_full(rw.s), rw.ph, tr, m_w1);
+                    mbar_wait_t(x_full(rx.s), rx.ph, tr, m_x);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        if (mine) {
+                            const uint32_t a_lo = xb + (uint32_t)((rx.s * kXStageBytes) >> 4);
+                            const uint32_t b_lo = wb + (uint32_t)((rw.s * kWStageBytes) >> 4);
+                            issue_mmas(tmem_base + (uint32_t)(m * kCm), desc0 + (uint64_t)a_lo, desc0 + (uint64_t)b_lo, idesc96, kb > 0 ? 1u : 0u, 4);
+                            umma_commit(x_empty(rx.s));
+                            umma_commit(w_empty(rw.s));
+                        } else {
+                            mbar_arrive(x_empty(rx.s));
+                            mbar_arrive(w_empty(rw.s));
+                        }
                     }
-                    umma_commit(w_empty(rw.s));
-                    umma_commit(x_empty(rx.s));
+                    __syncwarp();
                 }
+                if (mine && elect_one()) umma_commit(d1_full(m));
                 __syncwarp();
-                rx.next(kXStages);
-                rw.next(kWStages);
             }
-            if (elect_one()) umma_commit(d1_full);
-            __syncwarp();
-            // the D2 columns double as the P3 output buffers of the previous tile: wait until its epilogue drained them
-            mbar_wait(d3_empty(0), ((2u * it) & 1u) ^ 1u);
-            mbar_wait(d3_empty(1), ((2u * it) & 1u) ^ 1u);
-            mbar_wait(t1_ready, it & 1u);
+            // the D2[j] columns double as the P3 output buffers of the previous tile: wait until its epilogue drained them
+            mbar_wait_t(d3_empty(wi, 0), ((2u * it) & 1u) ^ 1u, tr, m_pre2);
+            mbar_wait_t(d3_empty(wi, 1), ((2u * it) & 1u) ^ 1u, tr, m_pre2);
+            // output M tile j reads t1 rows [128 j, 128 j + 127 + 2 P + 2]: halo M tiles j and j + 1 (with P = 64, M tile 1 also
+            // touches the first two rows of halo M tile 2 — only for the two padding columns, whose results are discarded)
+            mbar_wait_t(t1_ready(wi), it & 1u, tr, m_pre2);
+            mbar_wait_t(t1_ready(wi + 1), it & 1u, tr, m_pre2);
             tc_fence_after();
             // ---------------- P2 ----------------
             {
                 const uint32_t dcol = tmem_base + (uint32_t)(kD2Col + wi * kCm);
                 const uint32_t jrow = (uint32_t)wi * mrow;
                 for (int s = 0; s < 14; ++s) {
-                    mbar_wait(w_full(rw.s), rw.ph);
+                    mbar_wait_t(w_full(rw.s), rw.ph, tr, m_w2);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t b_lo = wb + (uint32_t)((rw.s * kWStageBytes) >> 4);
                         if (s < 9) {
-                            const uint32_t sh = (uint32_t)(((s / 3) * p.P + (s % 3)) * 8);     // rows * 128 B >> 4
+                            const uint32_t sh = (uint32_t)((((s / 3) << p.LP) + (s % 3)) * 8);     // rows * 128 B >> 4
                             issue_mmas(dcol, desc0 + (uint64_t)(t0b + jrow + sh), desc0 + (uint64_t)b_lo, idesc96, s > 0 ? 1u : 0u, 4);
                         } else {
                             for (int h = 0; h < 2; ++h) {
                                 const int t = 2 * (s - 9) + h;
                                 if (t < 9) {
-                                    const uint32_t sh = (uint32_t)(((t / 3) * p.P + (t % 3)) * 8);
+                                    const uint32_t sh = (uint32_t)((((t / 3) << p.LP) + (t % 3)) * 8);
                                     // plane 1 holds channels 64-95 (32 = two 16-channel steps); the weight plane holds tap t's tail
                                     // in its first 64 bytes when t is even, in the next 64 bytes when t is odd
                                     issue_mmas(dcol, desc0 + (uint64_t)(t1b + jrow + sh), desc0 + (uint64_t)(b_lo + (uint32_t)h * 4u), idesc96, 1u, 2);
@@ -218,141 +279,196 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
                     __syncwarp();
                     rw.next(kWStages);
                 }
-                if (elect_one()) umma_commit(d2_full);
+                if (elect_one()) umma_commit(d2_full(wi));
                 __syncwarp();
             }
-            mbar_wait(t2_ready, it & 1u);
+            // warp 2 issues the next tile's MMAs into D1[2]: its t1 must have left TMEM (warp 3 waited for it above)
+            if (wi == 0) mbar_wait_t(t1_ready(2), it & 1u, tr, m_t2);
+            mbar_wait_t(t2_ready(wi), it & 1u, tr, m_t2);
             tc_fence_after();
             // ---------------- P3 ----------------
             for (int blk = 0; blk < p.nblk3; ++blk) {
                 const int b = blk & 1;
                 const uint32_t use = 2u * it + (uint32_t)(blk >> 1);
-                mbar_wait(d3_empty(b), (use & 1u) ^ 1u);
+                mbar_wait_t(d3_empty(wi, b), (use & 1u) ^ 1u, tr, m_e3);
+                mbar_wait_t(w_full(rw.s), rw.ph, tr, m_w3);
                 tc_fence_after();
-                const uint32_t dcol = tmem_base + (uint32_t)(kD2Col + b * kCm + wi * kNB3);
-                for (int pl = 0; pl < 2; ++pl) {
-                    mbar_wait(w_full(rw.s), rw.ph);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t b_lo = wb + (uint32_t)((rw.s * kWStageBytes) >> 4);
-                        const uint32_t a_lo = (pl == 0 ? t0b : t1b) + (uint32_t)wi * mrow;
-                        issue_mmas(dcol, desc0 + (uint64_t)a_lo, desc0 + (uint64_t)b_lo, idesc48, pl > 0 ? 1u : 0u, pl == 0 ? 4 : 2);
-                        umma_commit(w_empty(rw.s));
-                    }
-                    __syncwarp();
-                    rw.next(kWStages);
+                if (elect_one()) {
+                    const uint32_t dcol = tmem_base + (uint32_t)(kD2Col + wi * kCm + b * kNB3);
+                    const uint32_t b_lo = wb + (uint32_t)((rw.s * kWStageBytes) >> 4);
+                    const uint32_t jrow = (uint32_t)wi * mrow;
+                    issue_mmas(dcol, desc0 + (uint64_t)(t0b + jrow), desc0 + (uint64_t)b_lo, idesc48, 0u, 4);
+                    issue_mmas(dcol, desc0 + (uint64_t)(t1b + jrow), desc0 + (uint64_t)(b_lo + (uint32_t)((kNB3 * 128) >> 4)), idesc48, 1u, 2);
+                    umma_commit(w_empty(rw.s));
+                    umma_commit(d3_full(wi, b));
                 }
-                if (elect_one()) umma_commit(d3_full(b));
                 __syncwarp();
+                rw.next(kWStages);
             }
+        }
+        if (tr && wi == 0) {
+            p.dbg[2] = m_w1; p.dbg[3] = m_x; p.dbg[4] = m_pre2; p.dbg[5] = m_w2; p.dbg[6] = m_t2; p.dbg[7] = m_e3; p.dbg[8] = m_w3;
+            p.dbg[9] = clock64() - m_begin; p.dbg[10] = it;
         }
     } else {
         // =========================== epilogue warps ===========================
         const int ew = warp - 4;
         const int quad = warp & 3;               // TMEM lane quadrant of this warp
-        const int half = ew >> 2;                // P1 / P2: column half [half * 48, +48); P3: M tile
+        const int set = ew >> 2;                 // M tile served: halo M tile `set` (all 96 columns) + half of halo M tile 2; output M tile `set`
         const uint32_t tlane = (uint32_t)(quad * 32) << 16;
         const float *b1s = bias_s, *b2s = bias_s + kCm, *b3s = bias_s + 2 * kCm;
-        const uint32_t plane[2] = {t_base, t_base + (uint32_t)p.t_bytes};
+        const uint32_t plane0 = t_base, plane1 = t_base + (uint32_t)kTBytes;
+        const int LP = p.LP, PM = p.P - 1;
+        uint32_t ra[16], rb[16];
+        // relu(acc + bias) (or zero) of 16 channels starting at ch -> bf16 -> this thread's row of the t planes
+        auto to_plane = [&](const uint32_t *r, int ch, const float *bias, bool keep, int q) {
+            float v[16];
+            const float4 *bs = reinterpret_cast<const float4 *>(bias + ch);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 b4 = bs[i];
+                v[4 * i] = keep ? fmaxf(__uint_as_float(r[4 * i]) + b4.x, 0.f) : 0.f;
+                v[4 * i + 1] = keep ? fmaxf(__uint_as_float(r[4 * i + 1]) + b4.y, 0.f) : 0.f;
+                v[4 * i + 2] = keep ? fmaxf(__uint_as_float(r[4 * i + 2]) + b4.z, 0.f) : 0.f;
+                v[4 * i + 3] = keep ? fmaxf(__uint_as_float(r[4 * i + 3]) + b4.w, 0.f) : 0.f;
+            }
+            const uint32_t rowa = (ch < kBlockK ? plane0 : plane1) + (uint32_t)q * 128u;
+            const int k16 = (ch & 63) >> 3, sw = q & 7;       // 16-byte chunk index inside the 128-byte row
+            sts128(rowa + (uint32_t)(((k16) ^ sw) << 4), pack8(v));
+            sts128(rowa + (uint32_t)(((k16 + 1) ^ sw) << 4), pack8(v + 8));
+        };
+        // n chunks of 16 accumulator columns starting at TMEM column col0 (channel ch0), one TMEM load in flight ahead
+        auto drain_to_plane = [&](uint32_t col0, int ch0, int n, const float *bias, bool keep, int q) {
+            tmem_ld16_issue(col0, ra);
+            for (int c = 0; c < n; c += 2) {
+                tmem_ld_wait(ra);
+                if (c + 1 < n) tmem_ld16_issue(col0 + (uint32_t)((c + 1) * 16), rb);
+                to_plane(ra, ch0 + c * 16, bias, keep, q);
+                if (c + 1 < n) {
+                    tmem_ld_wait(rb);
+                    if (c + 2 < n) tmem_ld16_issue(col0 + (uint32_t)((c + 2) * 16), ra);
+                    to_plane(rb, ch0 + (c + 1) * 16, bias, keep, q);
+                }
+            }
+        };
         griddep_wait();
         uint32_t it = 0;
-        uint32_t r0[16];
+        const bool tr = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
+        long long e_d1 = 0, e_d2 = 0, e_d3 = 0, e_p1 = 0, e_p2 = 0, e_p3 = 0;
+        const long long e_begin = tr ? clock64() : 0;
         for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
             const RbTile tc = rb_tile(p, tile);
+            // this thread's output pixel (P3) and its residual row
+            const int pos = set * 128 + quad * 32 + lane;
+            const int ty = pos >> LP, tx = pos & PM;
+            const int oy = tc.oy0 + ty, ox = tc.ox0 + tx;
+            const bool valid = tx < p.TW && oy < p.H && ox < p.W;
+            const int64_t pix = ((int64_t)tc.n * p.H + oy) * p.W + ox;
+            const bf16 *rp = p.res + pix * p.res_cstride + p.res_coff;
+            bf16 *yp = p.y + pix * p.y_cstride + p.y_coff;
             // ---------------- epilogue 1: D1 -> t1 (bf16, swizzled, zero outside the image) ----------------
-            mbar_wait(d1_full, it & 1u);
-            tc_fence_after();
-            for (int m = 0; m < 3; ++m) {
-                const int q = m * 128 + quad * 32 + lane;           // halo position
-                const int hr = q / p.P, hc = q - hr * p.P;
-                const int iy = tc.oy0 - 1 + hr, ix = tc.ox0 - 1 + hc;
-                const bool inside = hr < p.R + 2 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                const bool wr = q < p.t_rows;
-                for (int c = 0; c < 3; ++c) {
-                    const int ch = half * 48 + c * 16;
-                    tmem_ld16_issue(tmem_base + tlane + (uint32_t)(m * kCm + ch), r0);
-                    tmem_ld_wait(r0);
-                    float v[16];
+            for (int pass = 0; pass < 2; ++pass) {
+                const int mm = pass == 0 ? set : 2;
+                const int q = mm * 128 + quad * 32 + lane;           // halo position
+                const int iy = tc.oy0 - 1 + (q >> LP), ix = tc.ox0 - 1 + (q & PM);
+                const bool inside = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                const int ch0 = pass == 0 ? 0 : set * 48;
+                mbar_wait_t(d1_full(mm), it & 1u, tr, e_d1);
+                tc_fence_after();
+                const long long c0 = tr ? clock64() : 0;
+                drain_to_plane(tmem_base + tlane + (uint32_t)(mm * kCm + ch0), ch0, pass == 0 ? 6 : 3, b1s, inside, q);
+                if (tr) e_p1 += clock64() - c0;
+                tc_fence_before();
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t1_ready(mm));
+            }
+            // the residual of the first output block travels while P2 runs
+            uint4 rr[6];
+            auto load_res = [&](const bf16 *src) {
+                if (p.wide_io) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = inside ? fmaxf(__uint_as_float(r0[i]) + b1s[ch + i], 0.f) : 0.f;
-                    if (wr) {
-                        const uint32_t rowa = plane[ch >> 6] + (uint32_t)q * 128u;
-                        const int k16 = (ch & 63) >> 3, sw = q & 7;       // 16-byte chunk index inside the 128-byte row
-                        sts128(rowa + (uint32_t)(((k16) ^ sw) << 4), pack8(v));
-                        sts128(rowa + (uint32_t)(((k16 + 1) ^ sw) << 4), pack8(v + 8));
+                    for (int i = 0; i < 3; ++i) {
+                        const U8 w = ldg256(src + 16 * i);
+                        rr[2 * i] = make_uint4(w.v[0], w.v[1], w.v[2], w.v[3]);
+                        rr[2 * i + 1] = make_uint4(w.v[4], w.v[5], w.v[6], w.v[7]);
                     }
-                }
-            }
-            tc_fence_before();
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(t1_ready);
-            // ---------------- epilogue 2: D2 -> t2 (over t1) ----------------
-            mbar_wait(d2_full, it & 1u);
-            tc_fence_after();
-            for (int j = 0; j < 2; ++j) {
-                const int q = j * 128 + quad * 32 + lane;
-                for (int c = 0; c < 3; ++c) {
-                    const int ch = half * 48 + c * 16;
-                    tmem_ld16_issue(tmem_base + tlane + (uint32_t)(kD2Col + j * kCm + ch), r0);
-                    tmem_ld_wait(r0);
-                    float v[16];
+                } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(r0[i]) + b2s[ch + i], 0.f);
-                    const uint32_t rowa = plane[ch >> 6] + (uint32_t)q * 128u;
-                    const int k16 = (ch & 63) >> 3, sw = q & 7;
-                    sts128(rowa + (uint32_t)(((k16) ^ sw) << 4), pack8(v));
-                    sts128(rowa + (uint32_t)(((k16 + 1) ^ sw) << 4), pack8(v + 8));
+                    for (int i = 0; i < 6; ++i) rr[i] = reinterpret_cast<const uint4 *>(src)[i];
                 }
-            }
+            };
+#pragma unroll
+            for (int i = 0; i < 6; ++i) rr[i] = make_uint4(0, 0, 0, 0);
+            if (valid) load_res(rp);
+            // ---------------- epilogue 2: D2 -> t2 (over t1: every P2 MMA of BOTH output M tiles has completed) ----------------
+            mbar_wait_t(d2_full(0), it & 1u, tr, e_d2);
+            mbar_wait_t(d2_full(1), it & 1u, tr, e_d2);
+            tc_fence_after();
+            const long long c1 = tr ? clock64() : 0;
+            drain_to_plane(tmem_base + tlane + (uint32_t)(kD2Col + set * kCm), 0, 6, b2s, true, pos);
+            if (tr) e_p2 += clock64() - c1;
             tc_fence_before();
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(t2_ready);
+            if (lane == 0) mbar_arrive(t2_ready(set));
             // ---------------- epilogue 3: D3 blocks -> y = act(acc + b3 + res) ----------------
-            {
-                const int pos = half * 128 + quad * 32 + lane;
-                const int ty = pos / p.P, tx = pos - ty * p.P;
-                const int oy = tc.oy0 + ty, ox = tc.ox0 + tx;
-                const bool valid = ty < p.R && tx < p.TW && oy < p.H && ox < p.W;
-                const int64_t pix = ((int64_t)tc.n * p.H + oy) * p.W + ox;
-                const bf16 *rp = p.res + pix * p.res_cstride + p.res_coff;
-                bf16 *yp = p.y + pix * p.y_cstride + p.y_coff;
-                for (int blk = 0; blk < p.nblk3; ++blk) {
-                    const int b = blk & 1;
-                    const uint32_t use = 2u * it + (uint32_t)(blk >> 1);
-                    uint4 rr[6];
+            for (int blk = 0; blk < p.nblk3; ++blk) {
+                const int b = blk & 1;
+                const uint32_t use = 2u * it + (uint32_t)(blk >> 1);
+                uint4 cr[6];
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) rr[i] = make_uint4(0, 0, 0, 0);
-                    if (valid) {
+                for (int i = 0; i < 6; ++i) cr[i] = rr[i];
+                if (valid && blk + 1 < p.nblk3) load_res(rp + (blk + 1) * kNB3);      // one block ahead of its use
+                mbar_wait_t(d3_full(set, b), use & 1u, tr, e_d3);
+                tc_fence_after();
+                const long long c2 = tr ? clock64() : 0;
+                const uint32_t col0 = tmem_base + tlane + (uint32_t)(kD2Col + set * kCm + b * kNB3);
+                auto finish = [&](const uint32_t *r, int c) {
+                    if (!valid) return;
+                    float v[16], rs[16];
+                    unpack8(cr[2 * c], rs);
+                    unpack8(cr[2 * c + 1], rs + 8);
+                    const int co = blk * kNB3 + c * 16;
+                    const float4 *bs = reinterpret_cast<const float4 *>(b3s + co);
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) rr[i] = reinterpret_cast<const uint4 *>(rp + blk * kNB3)[i];
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b4 = bs[i];
+                        v[4 * i] = __uint_as_float(r[4 * i]) + b4.x + rs[4 * i];
+                        v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y + rs[4 * i + 1];
+                        v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z + rs[4 * i + 2];
+                        v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w + rs[4 * i + 3];
                     }
-                    mbar_wait(d3_full(b), use & 1u);
-                    tc_fence_after();
+                    if (p.final_relu) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        tmem_ld16_issue(tmem_base + tlane + (uint32_t)(kD2Col + b * kCm + half * kNB3 + c * 16), r0);
-                        tmem_ld_wait(r0);
-                        if (valid) {
-                            float v[16], r[16];
-                            unpack8(rr[2 * c], r);
-                            unpack8(rr[2 * c + 1], r + 8);
-                            const int co = blk * kNB3 + c * 16;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                v[i] = __uint_as_float(r0[i]) + b3s[co + i] + r[i];
-                                if (p.final_relu) v[i] = fmaxf(v[i], 0.f);
-                            }
-                            reinterpret_cast<uint4 *>(yp + co)[0] = pack8(v);
-                            reinterpret_cast<uint4 *>(yp + co)[1] = pack8(v + 8);
-                        }
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(d3_empty(b));
-                }
+                    if (p.wide_io) {
+                        stg256(yp + co, pack8(v), pack8(v + 8));
+                    } else {
+                        reinterpret_cast<uint4 *>(yp + co)[0] = pack8(v);
+                        reinterpret_cast<uint4 *>(yp + co)[1] = pack8(v + 8);
+                    }
+                };
+                tmem_ld16_issue(col0, ra);
+                tmem_ld_wait(ra);
+                tmem_ld16_issue(col0 + 16u, rb);
+                finish(ra, 0);
+                tmem_ld_wait(rb);
+                tmem_ld16_issue(col0 + 32u, ra);
+                finish(rb, 1);
+                tmem_ld_wait(ra);
+                // every TMEM read of this buffer has completed: the issuer may overwrite it while the last chunk is stored
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d3_empty(set, b));
+                finish(ra, 2);
+                if (tr) e_p3 += clock64() - c2;
             }
+        }
+        if (tr) {
+            p.dbg[11] = e_d1; p.dbg[12] = e_p1; p.dbg[13] = e_d2; p.dbg[14] = e_p2; p.dbg[15] = e_d3; p.dbg[16] = e_p3;
+            p.dbg[17] = clock64() - e_begin;
         }
     }
     tc_fence_before();
@@ -397,47 +513,33 @@ extern "C" int rgbd_rb_plan_create(const rgbd_rb_desc *d, rgbd_rb_plan **out) {
     p.kb1 = d->Cin / kBlockK;
     p.nblk3 = d->Cout / kNB3;
     p.final_relu = d->final_relu;
-    // tile geometry: R * P <= 256 output positions (two M tiles), (R + 2) * P + 2 <= 384 halo positions (three M tiles);
-    // fewest tiles wins (every tile streams the same weights), ties go to the wider tile (longer contiguous rows)
+    p.prefetch = getenv("RGBD_RB_NOPREFETCH") == nullptr;
+    p.wide_io = ((d->res_cstride | d->res_coff | d->y_cstride | d->y_coff) & 15) == 0 && (((uintptr_t)d->res | (uintptr_t)d->y) & 31) == 0;
+    p.dbg = nullptr;
+#ifdef RGBD_TIMING_PROBES
+    if (const char *e = getenv("RGBD_TC_TRACE")) p.dbg = (long long *)strtoull(e, nullptr, 0);
+#endif
+    // tile geometry: row pitch P = 32 or 64 positions (power of two: one M tile = 128 / P whole rows), 2 M tiles of output
+    // per tile, TW = P - 2 useful columns; the pitch that needs fewer tiles wins (ties: the wider one, longer rows)
     long best = -1;
-    for (int TW = 2; TW <= d->W && TW + 2 <= 256; ++TW) {
-        const int P = TW + 2;
-        int R = 256 / P;
-        while (R > 0 && (R + 2) * P + 2 > 384) --R;
-        if (R > d->H) R = d->H;
-        if (R < 1) continue;
-        {
-            const long xb = ((long)(R + 2) * P * 128 + 1023) / 1024 * 1024;
-            long tr = (258 + 2 * P + 7) / 8 * 8;
-            if (tr > 384) tr = 384;
-            const long tb = (tr * 128 + 1023) / 1024 * 1024;
-            if (kXStages * xb + 2 * tb + kWStages * kWStageBytes + 4096 > 227 * 1024) continue;
-        }
+    for (int P = 32; P <= 64; P *= 2) {
+        const int rpm = 128 / P, R = 2 * rpm, TW = P - 2;
         const long tiles = (long)((d->W + TW - 1) / TW) * (long)((d->H + R - 1) / R);
         if (best < 0 || tiles <= best) {
             best = tiles;
-            p.TW = TW; p.R = R; p.P = P;
+            p.TW = TW; p.R = R; p.P = P; p.rpm = rpm;
+            p.LP = P == 32 ? 5 : 6;
         }
-    }
-    if (best < 0) {
-        rgbd_set_error("rb: no tile geometry for %d x %d", d->H, d->W);
-        delete pl;
-        return RGBD_E_INVALID;
     }
     p.tiles_x = (d->W + p.TW - 1) / p.TW;
     p.tiles_y = (d->H + p.R - 1) / p.R;
     const long total = (long)d->N * p.tiles_x * p.tiles_y;
+    RGBD_CHECK_ARG(total < 2147483647L, "too many tiles");
     p.total_tiles = (int)total;
-    p.x_tx = (p.R + 2) * p.P * 128;
-    p.x_bytes = (p.x_tx + 1023) / 1024 * 1024;
-    p.t_rows = (258 + 2 * p.P + 7) / 8 * 8;                   // rows P2 can address: 128 + 127 + (2 P + 2) + 1
-    if (p.t_rows > 384) p.t_rows = 384;
-    p.t_bytes = (p.t_rows * 128 + 1023) / 1024 * 1024;
-    pl->smem = 1024 + (size_t)kXStages * p.x_bytes + 2 * (size_t)p.t_bytes + (size_t)kWStages * kWStageBytes +
-               8 * (2 * kXStages + 2 * kWStages) + 64 + 16 + 4 * (2 * kCm + kMaxCout) + 64;
-    // P1 reads three full M tiles (384 rows) from a stage: the last stage's over-read must stay inside the allocation
-    RGBD_CHECK_ARG((size_t)(kXStages - 1) * p.x_bytes + 384 * 128 <= (size_t)kXStages * p.x_bytes + 2 * (size_t)p.t_bytes,
-                   "internal: halo over-read leaves the allocation");
+    // [x ring | t plane 0 | t plane 1 | weight ring | barriers | TMEM slot | biases]; reads of t rows 384 / 385 (P = 64, padding
+    // columns only) fall into the next region of the same allocation
+    pl->smem = 1024 + (size_t)kXStages * kXStageBytes + 2 * (size_t)kTBytes + (size_t)kWStages * kWStageBytes +
+               8 * kRbBarriers + 16 + 4 * (2 * kCm + kMaxCout) + 64;
     if (pl->smem > 227 * 1024) {
         rgbd_set_error("rb: %zu bytes of shared memory needed", pl->smem);
         delete pl;
@@ -453,7 +555,7 @@ extern "C" int rgbd_rb_plan_create(const rgbd_rb_desc *d, rgbd_rb_plan **out) {
         cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
         cuuint64_t strides[3] = {(cuuint64_t)d->x_cstride * 2, (cuuint64_t)d->W * d->x_cstride * 2,
                                  (cuuint64_t)d->H * d->W * d->x_cstride * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)p.P, (cuuint32_t)(p.R + 2), 1};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)p.P, (cuuint32_t)p.rpm, 1};
         rc = encode_map(&p.xmap, reinterpret_cast<const char *>(d->x) + (int64_t)d->x_coff * 2, 4, dims, strides, box);
     }
     if (!rc) {   // W1: bf16 [1][96][Cin]
@@ -488,8 +590,8 @@ extern "C" int rgbd_rb_plan_create(const rgbd_rb_desc *d, rgbd_rb_plan **out) {
         }
     }
     if (getenv("RGBD_TC_VERBOSE"))
-        fprintf(stderr, "rb_fused: %dx%d Cin %d Cout %d | TW %d R %d P %d tiles %d x_bytes %d t_rows %d smem %zu\n", d->H, d->W, d->Cin,
-                d->Cout, p.TW, p.R, p.P, p.total_tiles, p.x_bytes, p.t_rows, pl->smem);
+        fprintf(stderr, "rb_fused: %dx%d Cin %d Cout %d | TW %d R %d P %d tiles %d smem %zu\n", d->H, d->W, d->Cin, d->Cout, p.TW,
+                p.R, p.P, p.total_tiles, pl->smem);
     *out = pl;
     return RGBD_OK;
 }

@@ -37,10 +37,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+#ifdef RGBD_MBAR_SOFT_TIMEOUT
+        // debugging aid (RGBD_BUILD_DEFINES=-DRGBD_MBAR_SOFT_TIMEOUT): report the barrier and carry on, so that the kernel
+        // ends and the message reaches the host (a trap discards the printf buffer)
+        if (clock64() - t0 > 100000000LL) {
+            if ((threadIdx.x & 31) == 0 || (threadIdx.x >> 5) < 2) {
+                unsigned long long ns;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+                printf("T %llu rgbd tc: mbarrier timeout block %d warp %d bar# %u parity %u\n", ns, blockIdx.x, threadIdx.x >> 5, (bar & 1023u) >> 3, parity);
+            }
+            return;
+        }
+#else
         if (clock64() - t0 > 4000000000LL) {  // ~2 s
             printf("rgbd conv_halo: mbarrier timeout (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
             __trap();
         }
+#endif
     }
 }
 // wait that adds the stalled cycles to *acc when tracing
@@ -206,6 +219,35 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
+// 32-byte global accesses (LDG.256 / STG.256).  In every epilogue a thread owns one pixel row, so the 32 accesses of a warp
+// instruction land in 32 different 128-byte lines; the load / store unit spends one wavefront per line however many bytes
+// it carries, so 32 bytes per lane halve the wavefronts of the 16-byte form.  The address must be 32-byte aligned.
+struct alignas(32) U8 {
+    uint32_t v[8];
+};
+__device__ __forceinline__ U8 ldg256(const void *p) {
+    U8 r;
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+// 16 consecutive bf16 of one pixel row as two uint4: one 32-byte load when the address allows, else two 16-byte loads
+__device__ __forceinline__ void ldg_2x128(const void *p, uint4 &a, uint4 &b) {
+    if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+        const U8 w = ldg256(p);
+        a = make_uint4(w.v[0], w.v[1], w.v[2], w.v[3]);
+        b = make_uint4(w.v[4], w.v[5], w.v[6], w.v[7]);
+    } else {
+        a = reinterpret_cast<const uint4 *>(p)[0];
+        b = reinterpret_cast<const uint4 *>(p)[1];
+    }
+}
+__device__ __forceinline__ void stg256(void *p, const uint4 &a, const uint4 &b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+                 "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
 // 16 consecutive bf16 channels of one pixel -> fp32 (vector path when 16-byte aligned and complete)
 __device__ __forceinline__ void load16_bf16(const __nv_bfloat16 *p, bool vec, int nvalid, float *v) {
     if (vec && nvalid >= 16) {
@@ -219,8 +261,12 @@ __device__ __forceinline__ void load16_bf16(const __nv_bfloat16 *p, bool vec, in
 template <typename T> __device__ __forceinline__ void store16(T *p, bool vec, int nvalid, const float *v);
 template <> __device__ __forceinline__ void store16<__nv_bfloat16>(__nv_bfloat16 *p, bool vec, int nvalid, const float *v) {
     if (vec && nvalid >= 16) {
-        reinterpret_cast<uint4 *>(p)[0] = pack8(v);
-        reinterpret_cast<uint4 *>(p)[1] = pack8(v + 8);
+        if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {      // 16 channels = 32 bytes: one STG.256 when the row is 32-byte aligned
+            stg256(p, pack8(v), pack8(v + 8));
+        } else {
+            reinterpret_cast<uint4 *>(p)[0] = pack8(v);
+            reinterpret_cast<uint4 *>(p)[1] = pack8(v + 8);
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i)
@@ -229,9 +275,18 @@ template <> __device__ __forceinline__ void store16<__nv_bfloat16>(__nv_bfloat16
 }
 template <> __device__ __forceinline__ void store16<float>(float *p, bool vec, int nvalid, const float *v) {
     if (vec && nvalid >= 16) {
+        if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+            uint4 q[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            reinterpret_cast<float4 *>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 4; ++i)
+                q[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+            stg256(p, q[0], q[1]);
+            stg256(p + 8, q[2], q[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4 *>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i)

@@ -6,6 +6,9 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, torch.nn as nn
 DEV = torch.device("cuda:0")
 NCU = os.environ.get("RGBD_NCU") == "1"
+dbg = torch.zeros(32, dtype=torch.int64, device=DEV)
+if not NCU and os.environ.get("RGBD_BUILD_DEFINES", "").find("RGBD_TIMING_PROBES") >= 0:
+    os.environ["RGBD_TC_TRACE"] = str(dbg.data_ptr())      # cycle counters of CTA 0 (development build of the library)
 from rgbd_b200.engine import Builder, PackedConv
 
 def timeit(b, name, extra=""):
@@ -32,7 +35,14 @@ def fused(N, H, W, cin=192, final_relu=False):
     if cin != 192:
         res = b.alloc(N, H, W, 192); res.buf.normal_()
     b.fused_block(*pcs, x, res=res, final_relu=final_relu)
+    dbg.zero_()
     timeit(b, f"fused 1x1-3x3-1x1 {cin}->96->96->192 @{H}x{W} N={N}")
+    d = dbg.cpu().tolist()
+    if d[10]:
+        n = d[10]
+        print(f"   CTA0 {n} tiles | MMA warp 2: {d[9]/n:.0f} cyc/tile; waits: w1 {d[2]/n:.0f} x {d[3]/n:.0f} d3_empty+t1_ready {d[4]/n:.0f} w2 {d[5]/n:.0f} "
+              f"t2_ready {d[6]/n:.0f} d3_empty(P3) {d[7]/n:.0f} w3 {d[8]/n:.0f} | producers: x_empty {d[0]/n:.0f} w_empty {d[1]/n:.0f} | "
+              f"epilogue warp 4: {d[17]/n:.0f} cyc/tile; wait d1 {d[11]/n:.0f} Ep1 {d[12]/n:.0f} wait d2 {d[13]/n:.0f} Ep2 {d[14]/n:.0f} wait d3 {d[15]/n:.0f} Ep3 {d[16]/n:.0f}", flush=True)
 
 def conv(name, mod, N, H, W, res=False, gate=False):
     b = Builder(DEV, torch.bfloat16, tensor_cores=True)

@@ -36,14 +36,16 @@ def _reference(c1, c2, c3, x, res, final_relu):
         return F.relu(y) if final_relu else y
 
 
-def _run(c1, c2, c3, x, res, final_relu, fused=True, same_res=False):
+def _run(c1, c2, c3, x, res, final_relu, fused=True, same_res=False, pads=(8, 16, 24)):
+    """pads: channel offsets of the x / res / y views inside wider buffers ((16, 32, 32): every pixel row 32-byte aligned,
+    the kernel's 256-bit load / store path; the default exercises the 128-bit path)"""
     from rgbd_b200.engine import Builder, PackedConv
     dev = torch.device(DEV)
     b = Builder(dev, torch.bfloat16, tensor_cores=True)
     pcs = [PackedConv(m, dev) for m in (c1, c2, c3)]
-    xv = _view(x)
-    rv = xv if same_res else _view(res, pad=16)
-    out = _view(torch.zeros(x.shape[0], c3.out_channels, *x.shape[2:]), pad=24, wide=40)
+    xv = _view(x, pad=pads[0])
+    rv = xv if same_res else _view(res, pad=pads[1])
+    out = _view(torch.zeros(x.shape[0], c3.out_channels, *x.shape[2:]), pad=pads[2], wide=40 if pads[2] == 24 else 32)
     if fused:
         assert b.can_fuse_block(*pcs, xv)
         b.fused_block(*pcs, xv, res=rv, out=out, final_relu=final_relu)
@@ -55,7 +57,7 @@ def _run(c1, c2, c3, x, res, final_relu, fused=True, same_res=False):
     b.prog.run()     # a second launch of the same plan (barrier phases / scheduler state start clean every launch)
     torch.cuda.synchronize()
     full = out.buf.float().cpu()
-    assert float(full[..., :24].abs().max()) == 0 and float(full[..., 24 + c3.out_channels:].abs().max()) == 0, \
+    assert float(full[..., :pads[2]].abs().max()) == 0 and float(full[..., pads[2] + c3.out_channels:].abs().max()) == 0, \
         "the kernel wrote outside its channel view"
     return out.torch().float().cpu().permute(0, 3, 1, 2)
 
@@ -67,6 +69,8 @@ CASES = [
     ("ru192_relu", 192, 2, 32, 40, True, True),
     ("rb384_skipres", 384, 1, 24, 44, False, False),         # RB(2N -> N): residual = output of the 1x1 skip conv
     ("rb192_many_tiles", 192, 3, 64, 80, False, True),       # > 148 tiles: every CTA walks several tiles
+    ("rb192_multi_tile_per_cta", 192, 8, 64, 80, False, True),   # 192 tiles on 148 CTAs: barrier phases across tiles
+    ("rb192_five_tiles_per_cta", 192, 2, 256, 320, True, True),   # 704 tiles
     ("rb192_tiny", 192, 1, 2, 2, False, True),
     ("rb192_tall_narrow", 192, 1, 70, 5, True, False),
 ]
@@ -84,6 +88,8 @@ def test_fused_block_vs_torch(name, cin, n, h, w, final_relu, same_res):
     got = _run(c1, c2, c3, x, res, final_relu, fused=True, same_res=same_res)
     assert got.shape == want.shape
     assert rel_err(got, want) < 6e-3, (name, rel_err(got, want))
+    wide = _run(c1, c2, c3, x, res, final_relu, fused=True, same_res=same_res, pads=(16, 32, 32))
+    assert torch.equal(wide, got), "the 256-bit and the 128-bit load / store paths must give the same bits"
     unfused = _run(c1, c2, c3, x, res, final_relu, fused=False, same_res=same_res)
     assert rel_err(got, unfused) < 6e-3, (name, rel_err(got, unfused))
 
