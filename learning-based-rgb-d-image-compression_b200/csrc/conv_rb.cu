@@ -7,12 +7,12 @@
 // C/2-channel intermediates kept ON CHIP: unfused, a block moves 960 channel-units per pixel through HBM
 // (x, t1 out/in, t2 out/in, x again, y); fused it moves 384 + halo.
 //
-// Geometry.  Positions are laid out with a power-of-two row pitch P (32 or 64), so one M tile of 128 positions is
-// rpm = 128 / P whole rows and position <-> (row, column) is a shift and a mask.  A tile produces 2 M tiles of output
-// (R = 2 rpm rows x TW = P - 2 useful columns); its one-pixel halo — (R + 2) rows x P columns starting one pixel up and
-// left — fits 3 M tiles.  One persistent CTA per SM walks the tiles.  Per tile, three GEMM phases share the tensor pipe:
-//   P1  t1 = relu(W1 x + b1) on the halo (3 M tiles, one after the other, so that the epilogue of a finished M tile runs
-//       under the MMAs of the next).  x arrives as 16 KB pieces {64 channels, P columns, rpm rows} = one (channel block, M
+// Geometry.  Positions are laid out with a row pitch of P = 32, so one M tile of 128 positions is rpm = 4 whole rows, one
+// epilogue warp (32 TMEM lanes) is one row, and position <-> (row, column) is a shift and a mask.  A tile produces 2 M
+// tiles of output (R = 8 rows x TW = 30 useful columns); its one-pixel halo — 10 rows x 32 columns starting one pixel up
+// and left — fits 3 M tiles (322 of their 384 rows are ever read).  One persistent CTA per SM walks the tiles.  Per tile, three GEMM phases share the tensor pipe:
+//   P1  t1 = relu(W1 x + b1) on the halo (3 M tiles: 0 and 1 together, one issuer warp each, then 2 — so that the epilogues
+//       of the first two run under the MMAs of the third).  x arrives as 16 KB pieces {64 channels, P columns, rpm rows} = one (channel block, M
 //       tile) each, through a 4-deep TMA ring; the NEXT tile's pieces are prefetched into L2 while this
 //       tile computes (cp.async.bulk.prefetch.tensor), so the ring refills at L2 latency, not HBM latency.  Accumulators
 //       D1[m] in TMEM columns [0, 288).  The epilogue warps turn D1 into bf16 t1 in shared memory (two 128-byte-row planes:
@@ -22,8 +22,11 @@
 //       through a UMMA descriptor whose start address is shifted by ky * P + kx rows (the halo trick of conv_halo.cu).
 //       D2[j] in TMEM columns [288, 480).  t2 overwrites t1 in shared memory (every P2 MMA has completed by then).
 //   P3  y = act(W3 t2 + b3 + res): four 48-channel output blocks per M tile, double buffered in the D2[j] region so that
-//       the epilogue of one block (residual from L2, bf16 NHWC stores) overlaps the MMAs of the next, and P1 of the NEXT
-//       tile (D1 columns are free again) overlaps the last epilogues.
+//       the epilogue of one block overlaps the MMAs of the next, and P1 of the NEXT tile (D1 columns are free again) overlaps
+//       the last epilogues.  The epilogue is bound by the load / store unit (a thread owns a pixel, so every global access
+//       of a warp lands in its own 128-byte line): the residual comes in with 32-byte loads, and the result leaves through a
+//       3 KB staging row per warp and ONE TMA store {48 channels, 30 columns, 1 row} per warp and block, which also clips
+//       the image border.
 // Weights stream from L2 through a 4-stage ring of 12 KB planes [96 rows x 64 K]; the K tails (channels 64-95) of two
 // consecutive 3x3 taps share one plane (no zero padding is fetched); a W3 stage holds both K planes of one output block.
 // Warp roles: 0 = x producer, 1 = weight producer, 2 / 3 = MMA issuers (output M tile j = warp - 2; halo M tiles 0 and 2
@@ -43,22 +46,24 @@ constexpr int kXStageBytes = 128 * 128;       // 16 KB: one M tile of positions 
 constexpr int kCm = 96;                       // bottleneck width (C / 2)
 constexpr int kWStageBytes = kCm * 128;       // 12 KB: 96 rows x 64 K (bf16)
 constexpr int kNB3 = 48;                      // output-channel block of P3
-constexpr int kTRows = 384;                   // rows of a t plane = 3 M tiles
-constexpr int kTBytes = kTRows * 128;
+constexpr int kP = 32, kLP = 5, kRpm = 4, kR = 8, kTW = 30;   // tile geometry (see above)
+constexpr int kTRows = 328;                   // rows of a t plane: P2 reads rows [0, 128 + 127 + 2 P + 2]
+constexpr int kTBytes = kTRows * 128;         // 41 KB (a multiple of 1024: plane 1 keeps the swizzle phase)
+constexpr int kYStageBytes = 32 * kNB3 * 2;   // per epilogue warp: 32 positions x 48 channels (bf16), packed
 constexpr uint32_t kRbTmemCols = 512;
 constexpr int kD2Col = 3 * kCm;               // 288
 constexpr int kMaxCout = 192;
 constexpr int kRbBarriers = 2 * kXStages + 2 * kWStages + 3 + 3 + 2 + 2 + 4 + 4;
 
 struct RbParams {
-    CUtensorMap xmap, w1map, w2map, w3map;
+    CUtensorMap xmap, w1map, w2map, w3map, ymap;
     const float *b1, *b2, *b3;
     const __nv_bfloat16 *res;
     __nv_bfloat16 *y;
     int32_t N, H, W, Cin, Cout;
     int32_t res_cstride, res_coff, y_cstride, y_coff;
-    int32_t TW, R, P, LP, rpm, tiles_x, tiles_y, total_tiles;
-    int32_t kb1, nblk3, final_relu, prefetch, wide_io;   // wide_io: res / y rows are 32-byte aligned
+    int32_t tiles_x, tiles_y, total_tiles;
+    int32_t kb1, nblk3, final_relu, prefetch, wide_io;   // wide_io: res rows are 32-byte aligned
     long long *dbg;   // optional cycle counters of CTA 0 (development builds: RGBD_TIMING_PROBES + RGBD_TC_TRACE), else NULL
 };
 
@@ -71,8 +76,8 @@ __device__ __forceinline__ RbTile rb_tile(const RbParams &p, int tile) {
     t.n = tile / per_img;
     const int r = tile - t.n * per_img;
     const int tyi = r / p.tiles_x;
-    t.oy0 = tyi * p.R;
-    t.ox0 = (r - tyi * p.tiles_x) * p.TW;
+    t.oy0 = tyi * kR;
+    t.ox0 = (r - tyi * p.tiles_x) * kTW;
     return t;
 }
 
@@ -107,6 +112,7 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
     const uint32_t tmem_slot = misc + 144u;
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
     float *bias_s = reinterpret_cast<float *>(smem_raw + (tmem_slot + 16u - raw));   // b1[96] | b2[96] | b3[Cout]
+    const uint32_t ystage_base = (tmem_slot + 16u + 4u * (uint32_t)(2 * kCm + kMaxCout) + 127u) & ~127u;   // 8 x kYStageBytes
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -158,17 +164,20 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
                 if (p.prefetch && tile + step < p.total_tiles) {
                     // the next tile's pieces start their way HBM -> L2 now: the ring can hold only 4 of its 9+ pieces ahead of time
                     const RbTile tn = rb_tile(p, tile + step);
-                    for (int m = 0; m < 3; ++m)
-                        for (int kb = 0; kb < p.kb1; ++kb) tma_prefetch_4d(&p.xmap, kb * kBlockK, tn.ox0 - 1, tn.oy0 - 1 + m * p.rpm, tn.n);
+                    for (int kb = 0; kb < p.kb1; ++kb)
+                        for (int m = 0; m < 3; ++m) tma_prefetch_4d(&p.xmap, kb * kBlockK, tn.ox0 - 1, tn.oy0 - 1 + m * kRpm, tn.n);
                 }
-                // halo M tile by halo M tile (all channel blocks of tile 0, then of tile 1, ...): D1[0] completes a third of the
-                // way into P1, so its epilogue runs under the MMAs of the other two
-                for (int m = 0; m < 3; ++m) {
-                    for (int kb = 0; kb < p.kb1; ++kb, rx.next(kXStages)) {
-                        mbar_wait_t(x_empty(rx.s), rx.ph ^ 1u, tr, wx);
-                        mbar_expect_tx(x_full(rx.s), (uint32_t)kXStageBytes);
-                        tma_load_4d(x_base + (uint32_t)(rx.s * kXStageBytes), &p.xmap, x_full(rx.s), kb * kBlockK, tc.ox0 - 1,
-                                    tc.oy0 - 1 + m * p.rpm, tc.n);
+                // halo M tiles 0 and 1 together (channel block by channel block: one issuer warp each, sharing the W1 stages),
+                // then M tile 2 alone: D1[0] and D1[1] complete two thirds of the way into P1, so their epilogues run under
+                // the MMAs of M tile 2
+                for (int part = 0; part < 2; ++part) {
+                    for (int kb = 0; kb < p.kb1; ++kb) {
+                        for (int m = part ? 2 : 0; m < (part ? 3 : 2); ++m, rx.next(kXStages)) {
+                            mbar_wait_t(x_empty(rx.s), rx.ph ^ 1u, tr, wx);
+                            mbar_expect_tx(x_full(rx.s), (uint32_t)kXStageBytes);
+                            tma_load_4d(x_base + (uint32_t)(rx.s * kXStageBytes), &p.xmap, x_full(rx.s), kb * kBlockK, tc.ox0 - 1,
+                                        tc.oy0 - 1 + m * kRpm, tc.n);
+                        }
                     }
                 }
             }
@@ -182,7 +191,7 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
             const bool tr = p.dbg != nullptr && blockIdx.x == 0;
             long long ww = 0;
             for (int tile = first; tile < p.total_tiles; tile += step) {
-                for (int mk = 0; mk < 3 * p.kb1; ++mk, rw.next(kWStages)) {      // W1 once per halo M tile (P1 runs M tile by M tile)
+                for (int mk = 0; mk < 2 * p.kb1; ++mk, rw.next(kWStages)) {      // W1 twice: for halo M tiles 0 + 1, then for M tile 2
                     mbar_wait_t(w_empty(rw.s), rw.ph ^ 1u, tr, ww);
                     mbar_expect_tx(w_full(rw.s), (uint32_t)kWStageBytes);
                     tma_load_3d(w_base + (uint32_t)(rw.s * kWStageBytes), &p.w1map, w_full(rw.s), (mk % p.kb1) * kBlockK, 0, 0);
@@ -217,30 +226,40 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
         const long long m_begin = tr ? clock64() : 0;
         for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
             // ---------------- P1 (D1[m] was drained by the epilogue of the previous tile: t1_ready waits below) ----------------
-            for (int m = 0; m < 3; ++m) {
-                const bool mine = (m == 1) == (wi == 1);
-                for (int kb = 0; kb < p.kb1; ++kb, rx.next(kXStages), rw.next(kWStages)) {
-                    // Both issuer warps wait for and release EVERY stage, also those whose MMAs the other warp issues: a
-                    // parity wait is only meaningful for a waiter that has seen the previous phase of the same barrier, so
-                    // nobody may skip a stage (and the producers must not run more than one ring round ahead of either warp).
+            // Both issuer warps wait for and release EVERY stage, also those whose MMAs the other warp issues: a parity wait is
+            // only meaningful for a waiter that has seen the previous phase of the same barrier, so nobody may skip a stage
+            // (and the producers must not run more than one ring round ahead of either warp).
+            for (int part = 0; part < 2; ++part) {
+                for (int kb = 0; kb < p.kb1; ++kb, rw.next(kWStages)) {
                     mbar_wait_t(w_full(rw.s), rw.ph, tr, m_w1);
-                    mbar_wait_t(x_full(rx.s), rx.ph, tr, m_x);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        if (mine) {
-                            const uint32_t a_lo = xb + (uint32_t)((rx.s * kXStageBytes) >> 4);
-                            const uint32_t b_lo = wb + (uint32_t)((rw.s * kWStageBytes) >> 4);
-                            issue_mmas(tmem_base + (uint32_t)(m * kCm), desc0 + (uint64_t)a_lo, desc0 + (uint64_t)b_lo, idesc96, kb > 0 ? 1u : 0u, 4);
-                            umma_commit(x_empty(rx.s));
-                            umma_commit(w_empty(rw.s));
-                        } else {
-                            mbar_arrive(x_empty(rx.s));
-                            mbar_arrive(w_empty(rw.s));
+                    const uint32_t b_lo = wb + (uint32_t)((rw.s * kWStageBytes) >> 4);
+                    bool issued = false;
+                    for (int m = part ? 2 : 0; m < (part ? 3 : 2); ++m, rx.next(kXStages)) {
+                        const bool mine = part ? wi == 0 : m == wi;
+                        mbar_wait_t(x_full(rx.s), rx.ph, tr, m_x);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            if (mine) {
+                                const uint32_t a_lo = xb + (uint32_t)((rx.s * kXStageBytes) >> 4);
+                                issue_mmas(tmem_base + (uint32_t)(m * kCm), desc0 + (uint64_t)a_lo, desc0 + (uint64_t)b_lo, idesc96, kb > 0 ? 1u : 0u, 4);
+                                umma_commit(x_empty(rx.s));
+                            } else {
+                                mbar_arrive(x_empty(rx.s));
+                            }
                         }
+                        __syncwarp();
+                        issued |= mine;
+                    }
+                    if (elect_one()) {
+                        if (issued) umma_commit(w_empty(rw.s));
+                        else mbar_arrive(w_empty(rw.s));
                     }
                     __syncwarp();
                 }
-                if (mine && elect_one()) umma_commit(d1_full(m));
+                if (elect_one()) {
+                    if (part == 0) umma_commit(d1_full(wi));
+                    else if (wi == 0) umma_commit(d1_full(2));
+                }
                 __syncwarp();
             }
             // the D2[j] columns double as the P3 output buffers of the previous tile: wait until its epilogue drained them
@@ -261,13 +280,13 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
                     if (elect_one()) {
                         const uint32_t b_lo = wb + (uint32_t)((rw.s * kWStageBytes) >> 4);
                         if (s < 9) {
-                            const uint32_t sh = (uint32_t)((((s / 3) << p.LP) + (s % 3)) * 8);     // rows * 128 B >> 4
+                            const uint32_t sh = (uint32_t)((((s / 3) << kLP) + (s % 3)) * 8);     // rows * 128 B >> 4
                             issue_mmas(dcol, desc0 + (uint64_t)(t0b + jrow + sh), desc0 + (uint64_t)b_lo, idesc96, s > 0 ? 1u : 0u, 4);
                         } else {
                             for (int h = 0; h < 2; ++h) {
                                 const int t = 2 * (s - 9) + h;
                                 if (t < 9) {
-                                    const uint32_t sh = (uint32_t)((((t / 3) << p.LP) + (t % 3)) * 8);
+                                    const uint32_t sh = (uint32_t)((((t / 3) << kLP) + (t % 3)) * 8);
                                     // plane 1 holds channels 64-95 (32 = two 16-channel steps); the weight plane holds tap t's tail
                                     // in its first 64 bytes when t is even, in the next 64 bytes when t is odd
                                     issue_mmas(dcol, desc0 + (uint64_t)(t1b + jrow + sh), desc0 + (uint64_t)(b_lo + (uint32_t)h * 4u), idesc96, 1u, 2);
@@ -318,7 +337,8 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
         const uint32_t tlane = (uint32_t)(quad * 32) << 16;
         const float *b1s = bias_s, *b2s = bias_s + kCm, *b3s = bias_s + 2 * kCm;
         const uint32_t plane0 = t_base, plane1 = t_base + (uint32_t)kTBytes;
-        const int LP = p.LP, PM = p.P - 1;
+        const int LP = kLP, PM = kP - 1;
+        const uint32_t ybuf = ystage_base + (uint32_t)(ew * kYStageBytes) + (uint32_t)(lane * kNB3 * 2);   // this thread's row of the warp's staging tile
         uint32_t ra[16], rb[16];
         // relu(acc + bias) (or zero) of 16 channels starting at ch -> bf16 -> this thread's row of the t planes
         auto to_plane = [&](const uint32_t *r, int ch, const float *bias, bool keep, int q) {
@@ -332,6 +352,7 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
                 v[4 * i + 2] = keep ? fmaxf(__uint_as_float(r[4 * i + 2]) + b4.z, 0.f) : 0.f;
                 v[4 * i + 3] = keep ? fmaxf(__uint_as_float(r[4 * i + 3]) + b4.w, 0.f) : 0.f;
             }
+            if (q >= kTRows) return;                          // halo rows 10 / 11 of M tile 2: never read
             const uint32_t rowa = (ch < kBlockK ? plane0 : plane1) + (uint32_t)q * 128u;
             const int k16 = (ch & 63) >> 3, sw = q & 7;       // 16-byte chunk index inside the 128-byte row
             sts128(rowa + (uint32_t)(((k16) ^ sw) << 4), pack8(v));
@@ -354,18 +375,19 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
         griddep_wait();
         uint32_t it = 0;
         const bool tr = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
-        long long e_d1 = 0, e_d2 = 0, e_d3 = 0, e_p1 = 0, e_p2 = 0, e_p3 = 0;
+        long long e_d1 = 0, e_d2 = 0, e_d3 = 0, e_p1 = 0, e_p2 = 0, e_p3 = 0, e_res = 0, e_bw = 0, e_st = 0, e_top = 0;
         const long long e_begin = tr ? clock64() : 0;
         for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
+            const long long qt = tr ? clock64() : 0;
             const RbTile tc = rb_tile(p, tile);
             // this thread's output pixel (P3) and its residual row
             const int pos = set * 128 + quad * 32 + lane;
             const int ty = pos >> LP, tx = pos & PM;
             const int oy = tc.oy0 + ty, ox = tc.ox0 + tx;
-            const bool valid = tx < p.TW && oy < p.H && ox < p.W;
+            const bool valid = tx < kTW && oy < p.H && ox < p.W;
             const int64_t pix = ((int64_t)tc.n * p.H + oy) * p.W + ox;
             const bf16 *rp = p.res + pix * p.res_cstride + p.res_coff;
-            bf16 *yp = p.y + pix * p.y_cstride + p.y_coff;
+            if (tr) e_top += clock64() - qt;
             // ---------------- epilogue 1: D1 -> t1 (bf16, swizzled, zero outside the image) ----------------
             for (int pass = 0; pass < 2; ++pass) {
                 const int mm = pass == 0 ? set : 2;
@@ -416,16 +438,17 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
             for (int blk = 0; blk < p.nblk3; ++blk) {
                 const int b = blk & 1;
                 const uint32_t use = 2u * it + (uint32_t)(blk >> 1);
+                const long long q0 = tr ? clock64() : 0;
                 uint4 cr[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) cr[i] = rr[i];
                 if (valid && blk + 1 < p.nblk3) load_res(rp + (blk + 1) * kNB3);      // one block ahead of its use
+                if (tr) e_res += clock64() - q0;
                 mbar_wait_t(d3_full(set, b), use & 1u, tr, e_d3);
                 tc_fence_after();
                 const long long c2 = tr ? clock64() : 0;
                 const uint32_t col0 = tmem_base + tlane + (uint32_t)(kD2Col + set * kCm + b * kNB3);
                 auto finish = [&](const uint32_t *r, int c) {
-                    if (!valid) return;
                     float v[16], rs[16];
                     unpack8(cr[2 * c], rs);
                     unpack8(cr[2 * c + 1], rs + 8);
@@ -443,13 +466,14 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    if (p.wide_io) {
-                        stg256(yp + co, pack8(v), pack8(v + 8));
-                    } else {
-                        reinterpret_cast<uint4 *>(yp + co)[0] = pack8(v);
-                        reinterpret_cast<uint4 *>(yp + co)[1] = pack8(v + 8);
-                    }
+                    sts128(ybuf + (uint32_t)(c * 32), pack8(v));
+                    sts128(ybuf + (uint32_t)(c * 32 + 16), pack8(v + 8));
                 };
+                // the TMA store of the previous block has read the staging row
+                const long long q1 = tr ? clock64() : 0;
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
+                if (tr) e_bw += clock64() - q1;
                 tmem_ld16_issue(col0, ra);
                 tmem_ld_wait(ra);
                 tmem_ld16_issue(col0 + 16u, rb);
@@ -463,12 +487,22 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d3_empty(set, b));
                 finish(ra, 2);
+                const long long q2 = tr ? clock64() : 0;
+                fence_async_smem();
+                __syncwarp();
+                if (tr) e_st += clock64() - q2;
+                if (lane == 0) {      // this warp's row of the tile: columns beyond the image and rows below it are clipped by TMA
+                    tma_store_4d(&p.ymap, ystage_base + (uint32_t)(ew * kYStageBytes), blk * kNB3, tc.ox0, tc.oy0 + (pos >> LP), tc.n);
+                    bulk_commit();
+                }
                 if (tr) e_p3 += clock64() - c2;
             }
         }
+        if (lane == 0) bulk_wait0();      // every TMA store of this warp has been written
         if (tr) {
             p.dbg[11] = e_d1; p.dbg[12] = e_p1; p.dbg[13] = e_d2; p.dbg[14] = e_p2; p.dbg[15] = e_d3; p.dbg[16] = e_p3;
             p.dbg[17] = clock64() - e_begin;
+            p.dbg[18] = e_res; p.dbg[19] = e_bw; p.dbg[20] = e_st; p.dbg[21] = e_top;
         }
     }
     tc_fence_before();
@@ -514,32 +548,20 @@ extern "C" int rgbd_rb_plan_create(const rgbd_rb_desc *d, rgbd_rb_plan **out) {
     p.nblk3 = d->Cout / kNB3;
     p.final_relu = d->final_relu;
     p.prefetch = getenv("RGBD_RB_NOPREFETCH") == nullptr;
-    p.wide_io = ((d->res_cstride | d->res_coff | d->y_cstride | d->y_coff) & 15) == 0 && (((uintptr_t)d->res | (uintptr_t)d->y) & 31) == 0;
+    p.wide_io = ((d->res_cstride | d->res_coff) & 15) == 0 && ((uintptr_t)d->res & 31) == 0;
     p.dbg = nullptr;
 #ifdef RGBD_TIMING_PROBES
     if (const char *e = getenv("RGBD_TC_TRACE")) p.dbg = (long long *)strtoull(e, nullptr, 0);
 #endif
-    // tile geometry: row pitch P = 32 or 64 positions (power of two: one M tile = 128 / P whole rows), 2 M tiles of output
-    // per tile, TW = P - 2 useful columns; the pitch that needs fewer tiles wins (ties: the wider one, longer rows)
-    long best = -1;
-    for (int P = 32; P <= 64; P *= 2) {
-        const int rpm = 128 / P, R = 2 * rpm, TW = P - 2;
-        const long tiles = (long)((d->W + TW - 1) / TW) * (long)((d->H + R - 1) / R);
-        if (best < 0 || tiles <= best) {
-            best = tiles;
-            p.TW = TW; p.R = R; p.P = P; p.rpm = rpm;
-            p.LP = P == 32 ? 5 : 6;
-        }
-    }
-    p.tiles_x = (d->W + p.TW - 1) / p.TW;
-    p.tiles_y = (d->H + p.R - 1) / p.R;
+    // fixed tile geometry (kP, kR, kTW above): 8 rows x 30 useful columns of output per tile
+    p.tiles_x = (d->W + kTW - 1) / kTW;
+    p.tiles_y = (d->H + kR - 1) / kR;
     const long total = (long)d->N * p.tiles_x * p.tiles_y;
     RGBD_CHECK_ARG(total < 2147483647L, "too many tiles");
     p.total_tiles = (int)total;
-    // [x ring | t plane 0 | t plane 1 | weight ring | barriers | TMEM slot | biases]; reads of t rows 384 / 385 (P = 64, padding
-    // columns only) fall into the next region of the same allocation
+    // [x ring | t plane 0 | t plane 1 | weight ring | barriers | TMEM slot | biases | output staging rows]
     pl->smem = 1024 + (size_t)kXStages * kXStageBytes + 2 * (size_t)kTBytes + (size_t)kWStages * kWStageBytes +
-               8 * kRbBarriers + 16 + 4 * (2 * kCm + kMaxCout) + 64;
+               8 * kRbBarriers + 16 + 4 * (2 * kCm + kMaxCout) + 128 + 8 * (size_t)kYStageBytes + 64;
     if (pl->smem > 227 * 1024) {
         rgbd_set_error("rb: %zu bytes of shared memory needed", pl->smem);
         delete pl;
@@ -555,7 +577,7 @@ extern "C" int rgbd_rb_plan_create(const rgbd_rb_desc *d, rgbd_rb_plan **out) {
         cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
         cuuint64_t strides[3] = {(cuuint64_t)d->x_cstride * 2, (cuuint64_t)d->W * d->x_cstride * 2,
                                  (cuuint64_t)d->H * d->W * d->x_cstride * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)p.P, (cuuint32_t)p.rpm, 1};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)kP, (cuuint32_t)kRpm, 1};
         rc = encode_map(&p.xmap, reinterpret_cast<const char *>(d->x) + (int64_t)d->x_coff * 2, 4, dims, strides, box);
     }
     if (!rc) {   // W1: bf16 [1][96][Cin]
@@ -576,6 +598,13 @@ extern "C" int rgbd_rb_plan_create(const rgbd_rb_desc *d, rgbd_rb_plan **out) {
         cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)kNB3, 1};
         rc = encode_map(&p.w3map, d->w3, 3, dims, strides, box);
     }
+    if (!rc) {   // y: bf16 NHWC view, stored by TMA as packed boxes {48 channels, 30 columns, 1 row} (no swizzle)
+        cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+        cuuint64_t strides[3] = {(cuuint64_t)d->y_cstride * 2, (cuuint64_t)d->W * d->y_cstride * 2,
+                                 (cuuint64_t)d->H * d->W * d->y_cstride * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kNB3, (cuuint32_t)kTW, 1, 1};
+        rc = encode_map(&p.ymap, reinterpret_cast<char *>(d->y) + (int64_t)d->y_coff * 2, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    }
     if (rc) {
         delete pl;
         return rc;
@@ -590,8 +619,7 @@ extern "C" int rgbd_rb_plan_create(const rgbd_rb_desc *d, rgbd_rb_plan **out) {
         }
     }
     if (getenv("RGBD_TC_VERBOSE"))
-        fprintf(stderr, "rb_fused: %dx%d Cin %d Cout %d | TW %d R %d P %d tiles %d smem %zu\n", d->H, d->W, d->Cin, d->Cout, p.TW,
-                p.R, p.P, p.total_tiles, pl->smem);
+        fprintf(stderr, "rb_fused: %dx%d Cin %d Cout %d | tiles %d smem %zu\n", d->H, d->W, d->Cin, d->Cout, p.total_tiles, pl->smem);
     *out = pl;
     return RGBD_OK;
 }

@@ -542,7 +542,9 @@ class ELIC(nn.Module):
             ev.record(stream)
             p.io["h2d_done"] = ev
             p.run(self.use_cuda_graph)
-            p.io["state_host"].copy_(p.io["state"], non_blocking=True)
+            # (zero-copy stores by a tiny kernel, not the copy engine: see ELIC_united.decompress_async)
+            L.call("rgbd_copy_view", p.io["state"].data_ptr(), p.io["state_host"].data_ptr(), L.DT_F32, p.io["n_streams"], 4, 4, 0,
+                   4, 0, ctypes.c_void_p(stream.cuda_stream))
             done = torch.cuda.Event()
             done.record(stream)
         return _SingleDecompressHandle(p, stream, done, lens)

@@ -845,15 +845,23 @@ class ELIC_united(nn.Module):
         stream = self._slot_stream(slot)
         self._order_after_producer(stream, rgb, depth)
         with torch.cuda.device(self.device), torch.cuda.stream(stream):
-            p.io["rgb"].copy_(rgb, non_blocking=True)
-            p.io["depth"].copy_(depth, non_blocking=True)
+            for name, src in (("rgb", rgb), ("depth", depth)):
+                if src.is_cuda or B == 1:
+                    p.io[name].copy_(src, non_blocking=True)
+                else:
+                    # host images: one H2D copy per image, so that a big batch does not hold the copy engine for
+                    # milliseconds while other pipeline slots' small transfers (stream words, decoder states) wait behind it
+                    for i in range(B):
+                        p.io[name][i].copy_(src[i], non_blocking=True)
             p.run(self.use_cuda_graph)
             if "gather_host" not in p.io:
                 p.io["gather_host"] = torch.empty((p.io["n_streams"] + p.io["gather_cap"],), dtype=torch.int32,
                                                   device="cpu", pin_memory=True)
             gh = p.io["gather_host"]
-            # one kernel packs the counts and every stream's tail straight into pinned host memory (zero-copy
-            # stores over PCIe): the strings are complete on the host when `done` fires, no second D2H round trip
+            # one kernel packs the counts and every stream's tail straight into pinned host memory (zero-copy stores over
+            # PCIe): the strings are complete on the host when `done` fires.  Deliberately NOT a DMA copy: the copy engine
+            # serves its queue in order, and behind other slots' bulk transfers (a job's reconstruction is 126 MB) this small,
+            # latency-critical transfer waited milliseconds (measured on B200: 304 -> 259 pairs/s end to end).
             L.call("rgbd_gather_streams", *p.io["gather_args"], gh.data_ptr(), p.io["gather_cap"],
                    ctypes.c_void_p(stream.cuda_stream))
             done = torch.cuda.Event()
@@ -968,7 +976,10 @@ class ELIC_united(nn.Module):
             p.run(self.use_cuda_graph)
             if "state_host" not in p.io:
                 p.io["state_host"] = torch.empty((p.io["n_streams"], 2), dtype=torch.int64, device="cpu", pin_memory=True)
-            p.io["state_host"].copy_(p.io["state"], non_blocking=True)
+            # decoder end states -> pinned host memory by a tiny kernel (zero-copy stores), not by the copy engine: see
+            # compress_async — `done` must not wait behind other slots' bulk D2H
+            L.call("rgbd_copy_view", p.io["state"].data_ptr(), p.io["state_host"].data_ptr(), L.DT_F32, p.io["n_streams"], 4, 4, 0,
+                   4, 0, ctypes.c_void_p(stream.cuda_stream))
             done = torch.cuda.Event()
             done.record(stream)
         return _DecompressHandle(p, stream, done, lens)

@@ -60,7 +60,8 @@ class RoundTripPipeline:
         """Plans are built and CUDA graphs captured from ONE thread (stream capture is process-global): the first
         time a shape is seen, every slot runs one job to completion before the worker threads start."""
         rgb, depth = self._input(0, 0, jobs[0], stage_input)
-        key = (tuple(rgb.shape), str(rgb.device))
+        device = next(self.net.parameters()).device      # (the inputs may be pinned host tensors)
+        key = (tuple(rgb.shape), str(device))
         if key in self._ready:
             return
         net, S = self.net, self.S
@@ -69,7 +70,7 @@ class RoundTripPipeline:
             c = net.compress_async(rgb, depth, slot=slot).result()
         for slot in range(self.D):
             net.decompress_async(c["r_strings"], c["d_strings"], c["shape"], slot=S + slot).result(clone=False)
-        torch.cuda.synchronize(rgb.device)
+        torch.cuda.synchronize(device)
         self._ready.add(key)
 
     # ------------------------------------------------------------------ public

@@ -42,7 +42,7 @@ def fused(N, H, W, cin=192, final_relu=False):
         n = d[10]
         print(f"   CTA0 {n} tiles | MMA warp 2: {d[9]/n:.0f} cyc/tile; waits: w1 {d[2]/n:.0f} x {d[3]/n:.0f} d3_empty+t1_ready {d[4]/n:.0f} w2 {d[5]/n:.0f} "
               f"t2_ready {d[6]/n:.0f} d3_empty(P3) {d[7]/n:.0f} w3 {d[8]/n:.0f} | producers: x_empty {d[0]/n:.0f} w_empty {d[1]/n:.0f} | "
-              f"epilogue warp 4: {d[17]/n:.0f} cyc/tile; wait d1 {d[11]/n:.0f} Ep1 {d[12]/n:.0f} wait d2 {d[13]/n:.0f} Ep2 {d[14]/n:.0f} wait d3 {d[15]/n:.0f} Ep3 {d[16]/n:.0f}", flush=True)
+              f"epilogue warp 4: {d[17]/n:.0f} cyc/tile; wait d1 {d[11]/n:.0f} Ep1 {d[12]/n:.0f} wait d2 {d[13]/n:.0f} Ep2 {d[14]/n:.0f} wait d3 {d[15]/n:.0f} Ep3 {d[16]/n:.0f} [in Ep3: staging-free wait {d[19]/n:.0f} fence {d[20]/n:.0f}] residual regs+issue {d[18]/n:.0f} tile setup {d[21]/n:.0f}", flush=True)
 
 def conv(name, mod, N, H, W, res=False, gate=False):
     b = Builder(DEV, torch.bfloat16, tensor_cores=True)
