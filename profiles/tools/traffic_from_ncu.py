@@ -35,7 +35,7 @@ def main():
     rows = parse(path)
     agg = {}
     for r in rows:
-        base = r["name"].split("(")[0].split("<")[0]
+        base = r["name"].replace("void ", "").replace("<unnamed>::", "").split("(")[0].split("<")[0]
         a = agg.setdefault(base, [0, 0.0, 0.0, 0.0])
         a[0] += 1
         a[1] += r.get("gpu__time_duration.sum", 0.0)
@@ -45,7 +45,7 @@ def main():
     print(f"| kernel | launches | total ms | share | dram read MB | dram write MB |\n|---|---:|---:|---:|---:|---:|")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"| {k} | {a[0]} | {a[1] / 1e3:.3f} | {100 * a[1] / tot:.1f}% | {a[2] / 1e6:.1f} | {a[3] / 1e6:.1f} |")
-    conv = [a for k, a in agg.items() if k.startswith("conv_") or "bottleneck" in k]
+    conv = [a for k, a in agg.items() if k.startswith("conv_") or k.startswith("rb_fused")]
     dram = sum(a[2] + a[3] for a in conv)
     out = os.path.join(ROOT, "profiles", "r02_traffic.json")
     entries = json.load(open(out)) if os.path.exists(out) else []
