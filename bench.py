@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--model", default="ELIC_united", choices=sorted(MODELS))
     ap.add_argument("--batch", type=int, default=0, help="pairs per job (default: as many as fit the HBM budget)")
     ap.add_argument("--precision", default=os.environ.get("RGBD_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--slots", type=int, default=8, help="jobs in flight per GPU (own launch plan + CUDA stream each)")
+    ap.add_argument("--slots", type=int, default=5, help="jobs in flight per GPU (own launch plan + CUDA stream each)")
     ap.add_argument("--jobs-per-step", type=int, default=0, help="jobs of --batch pairs per GPU and step (default: --slots)")
     ap.add_argument("--total-pairs", type=int, default=0,
                     help="strong scaling (BASELINE configs[2]): this many pairs per step in total, sharded "
@@ -322,8 +322,10 @@ def run_b200(args):
     elif args.precision == "fp32":
         candidates = [2, 1]
     else:
-        b0 = max(1, int(24 * (512 * 640) / (Hp * Wp) * 16 / (S + D)))
-        b0 = min(b0, 24)
+        # measured on B200 (profiles/README.md, round 2): at the same HBM footprint, 5 + 5 plans of 40 pairs beat 8 + 8 of 24
+        # (the 32x40 context-model launches fill the GPU better); jobs beyond 48 pairs gain nothing more
+        b0 = 24 * (512 * 640) / (Hp * Wp) * 16 / (S + D)
+        b0 = max(1, min(48, int(round(b0 / 4) * 4) if b0 >= 16 else int(b0)))
         if own is not None:
             # strong scaling: equal jobs only (a ragged last job would need a second set of launch plans per slot)
             divs = [d_ for d_ in range(1, own + 1) if own % d_ == 0 and d_ <= b0]
