@@ -260,8 +260,10 @@ __device__ __forceinline__ void stg256(void *p, const uint4 &a, const uint4 &b) 
 // 16 consecutive bf16 channels of one pixel -> fp32 (vector path when 16-byte aligned and complete)
 __device__ __forceinline__ void load16_bf16(const __nv_bfloat16 *p, bool vec, int nvalid, float *v) {
     if (vec && nvalid >= 16) {
-        unpack8(reinterpret_cast<const uint4 *>(p)[0], v);
-        unpack8(reinterpret_cast<const uint4 *>(p)[1], v + 8);
+        uint4 a, b;
+        ldg_2x128(p, a, b);       // one 32-byte load when the address allows
+        unpack8(a, v);
+        unpack8(b, v + 8);
     } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = i < nvalid ? __bfloat162float(p[i]) : 0.f;

@@ -186,6 +186,23 @@ class ELIC_united(nn.Module):
             self._packed[key] = PackedConv(mod, self.device, in_perm, split3, s2d)
         return self._packed[key]
 
+    def _pc_concat(self, first, second):
+        """One 1x1 conv over the channel concatenation [x_first | x_second]: weights [W_first | W_second] along K, biases
+        summed.  y = W_first x_first + W_second x_second + (b_first + b_second) in ONE accumulation — the skip conv and the
+        last conv of a widening / narrowing ResidualBottleneck (res_blk.py:7-27) become one launch, and their sum is formed
+        in the fp32 accumulator instead of through a bf16 round trip."""
+        if self._packed is None:
+            self._packed = {}
+        key = ("concat", id(first), id(second))
+        if key not in self._packed:
+            assert first.kernel_size == (1, 1) and second.kernel_size == (1, 1) and first.out_channels == second.out_channels
+            m = nn.Conv2d(first.in_channels + second.in_channels, first.out_channels, 1)
+            with torch.no_grad():
+                m.weight.copy_(torch.cat([first.weight.detach().float().cpu(), second.weight.detach().float().cpu()], dim=1))
+                m.bias.copy_(first.bias.detach().float().cpu() + second.bias.detach().float().cpu())
+            self._packed[key] = PackedConv(m, self.device)
+        return self._packed[key]
+
     def _dev32(self, key, make):
         if key not in self._aux:
             self._aux[key] = make().detach().to(device=self.device, dtype=torch.float32).contiguous()
@@ -203,6 +220,15 @@ class ELIC_united(nn.Module):
                 b.release(idn)
             return y
         t1 = b.conv(self._pc(m.branch[0]), x, act=RELU)
+        mid = m.branch[2].out_channels
+        if (m.skip is not None and b.tensor_cores and getattr(x.buf, "_rgbd_spare", 0) >= mid and x.coff + x.C + mid <= x.cstride
+                and x.dtype == torch.bfloat16 and (x.coff + x.C) % 8 == 0 and m.skip.bias is not None
+                and m.branch[4].bias is not None):
+            # x sits in a buffer with `mid` spare channels behind it (see _transform): the 3x3 writes t2 there, and the
+            # skip conv + last conv + add become ONE 1x1 conv over [x | t2] (K = Cin + mid)
+            t2 = b.conv(self._pc(m.branch[2]), t1, out=View(x.buf, x.coff + x.C, mid), act=RELU)
+            b.release(t1)
+            return b.conv(self._pc_concat(m.skip, m.branch[4]), View(x.buf, x.coff, x.C + mid), out=out)
         t2 = b.conv(self._pc(m.branch[2]), t1, act=RELU)
         b.release(t1)
         if m.skip is not None:
@@ -287,16 +313,26 @@ class ELIC_united(nn.Module):
                 # r, d are views [0:N] of 2N-wide buffers (depth always; rgb only when bidirectional)
                 if isinstance(rm, BiSpf):
                     self._bispf(b, rm, r, d, View(r.buf, N, N), View(d.buf, N, N))
-                    r = View(r.buf)
+                    r = View(r.buf, 0, 2 * N)
                 else:
                     self._bispf(b, rm, r, d, None, View(d.buf, N, N))
-                d = View(d.buf)
+                d = View(d.buf, 0, 2 * N)
                 continue
+
+            # ... and is the module after that bi_spf a ResidualBottleneck(2N -> N)?  Then the 2N-wide concat buffer gets
+            # N / ... spare channels for that block's bottleneck tensor (see _rb: skip conv + last conv as one launch)
+            after = rgb_seq[i + 2] if i + 2 < n else None
+            spare_r = after.branch[2].out_channels if feeds_spf and isinstance(after, ResidualBottleneck) and after.skip is not None else 0
+            after_d = depth_seq[i + 2] if i + 2 < n else None
+            spare_d = after_d.branch[2].out_channels if feeds_spf and isinstance(after_d, ResidualBottleneck) and after_d.skip is not None else 0
 
             def out_for(is_rgb, Hh, Ww, Cc):
                 wide = feeds_spf and (self.cross or not is_rgb)
                 if wide:
-                    return View(b.alloc(r.N, Hh, Ww, 2 * Cc).buf, 0, Cc)
+                    spare = (spare_r if is_rgb else spare_d) if b.tensor_cores else 0
+                    wide_buf = b.alloc(r.N, Hh, Ww, 2 * Cc + spare).buf
+                    wide_buf._rgbd_spare = spare          # channels behind the 2N-wide concat that _rb may use
+                    return View(wide_buf, 0, Cc)
                 return None
 
             def step(mod, x, is_rgb):
