@@ -140,6 +140,8 @@ typedef struct rgbd_rb_desc {
     int32_t res_cstride, res_coff, y_cstride, y_coff;
     int32_t final_relu;
     int32_t _pad;
+    void *sched_ws;                /* one zero-initialised int32 in device memory per plan: tile counter of the persistent
+                                    * kernel's dynamic scheduler (left at zero by every launch), as rgbd_conv_desc.sched_ws */
 } rgbd_rb_desc;
 typedef struct rgbd_rb_plan rgbd_rb_plan;
 int rgbd_rb_plan_create(const rgbd_rb_desc *d, rgbd_rb_plan **out);

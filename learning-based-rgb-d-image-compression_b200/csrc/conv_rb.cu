@@ -53,7 +53,8 @@ constexpr int kYStageBytes = 32 * kNB3 * 2;   // per epilogue warp: 32 positions
 constexpr uint32_t kRbTmemCols = 512;
 constexpr int kD2Col = 3 * kCm;               // 288
 constexpr int kMaxCout = 192;
-constexpr int kRbBarriers = 2 * kXStages + 2 * kWStages + 3 + 3 + 2 + 2 + 4 + 4;
+constexpr int kTileQ = 4;                     // depth of the CTA's tile queue (dynamic scheduler)
+constexpr int kRbBarriers = 2 * kXStages + 2 * kWStages + 3 + 3 + 2 + 2 + 4 + 4 + 2 * kTileQ;
 
 struct RbParams {
     CUtensorMap xmap, w1map, w2map, w3map, ymap;
@@ -63,7 +64,8 @@ struct RbParams {
     int32_t N, H, W, Cin, Cout;
     int32_t res_cstride, res_coff, y_cstride, y_coff;
     int32_t tiles_x, tiles_y, total_tiles;
-    int32_t kb1, nblk3, final_relu, prefetch, wide_io;   // wide_io: res rows are 32-byte aligned
+    int32_t kb1, nblk3, final_relu, prefetch, static_tiles, wide_io;   // wide_io: res rows are 32-byte aligned
+    int32_t *sched;   // tile counter (device memory, zero between launches)
     long long *dbg;   // optional cycle counters of CTA 0 (development builds: RGBD_TIMING_PROBES + RGBD_TC_TRACE), else NULL
 };
 
@@ -109,10 +111,13 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
     auto t2_ready = [&](int j) { return misc + 64u + 8u * (uint32_t)j; };
     auto d3_full = [&](int j, int b) { return misc + 80u + 8u * (uint32_t)(2 * j + b); };
     auto d3_empty = [&](int j, int b) { return misc + 112u + 8u * (uint32_t)(2 * j + b); };
-    const uint32_t tmem_slot = misc + 144u;
+    auto tq_full = [&](int q) { return misc + 144u + 8u * (uint32_t)q; };
+    auto tq_empty = [&](int q) { return misc + 144u + 8u * (uint32_t)(kTileQ + q); };
+    const uint32_t tmem_slot = misc + 144u + 16u * (uint32_t)kTileQ;
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
-    float *bias_s = reinterpret_cast<float *>(smem_raw + (tmem_slot + 16u - raw));   // b1[96] | b2[96] | b3[Cout]
-    const uint32_t ystage_base = (tmem_slot + 16u + 4u * (uint32_t)(2 * kCm + kMaxCout) + 127u) & ~127u;   // 8 x kYStageBytes
+    volatile int *tq_s = reinterpret_cast<volatile int *>(smem_raw + (tmem_slot + 16u - raw));   // kTileQ tile indices
+    float *bias_s = reinterpret_cast<float *>(smem_raw + (tmem_slot + 32u - raw));   // b1[96] | b2[96] | b3[Cout]
+    const uint32_t ystage_base = (tmem_slot + 32u + 4u * (uint32_t)(2 * kCm + kMaxCout) + 127u) & ~127u;   // 8 x kYStageBytes
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -136,6 +141,11 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
                 mbar_init(d3_empty(j, b), 4);
             }
         }
+        // tile queue: filled by the x producer, read by the weight producer, the two issuer warps and the epilogue warps
+        for (int q = 0; q < kTileQ; ++q) {
+            mbar_init(tq_full(q), 1);
+            mbar_init(tq_empty(q), 1 + 2 + 8);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, kRbTmemCols);
@@ -150,7 +160,18 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    const int first = (int)blockIdx.x, step = (int)gridDim.x;
+    // Dynamic tile scheduler (as in conv_halo.cu): tiles are handed out in index order from a global counter, so a CTA that
+    // starts late — its SM was busy with rANS coder blocks of another pipeline slot — does not hold the grid back; the others
+    // take its share.  The x producer draws the tiles (one ahead, for the L2 prefetch) and publishes them through a small
+    // queue; every other role reads the k-th entry.  Which CTA computes a tile has no effect on the result.
+    auto next_tile = [&](int k) -> int {      // consumers: all lanes of the calling warp
+        const int q = k % kTileQ;
+        mbar_wait(tq_full(q), (uint32_t)((k / kTileQ) & 1));
+        const int t = tq_s[q];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tq_empty(q));
+        return t;
+    };
 
     if (warp == 0) {
         // =========================== x producer: one (channel block, halo M tile) piece per stage ===========================
@@ -159,11 +180,34 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
             const bool tr = p.dbg != nullptr && blockIdx.x == 0;
             long long wx = 0;
             griddep_wait();
-            for (int tile = first; tile < p.total_tiles; tile += step) {
+            int drawn = 0;
+            auto draw = [&]() -> int {
+                if (p.static_tiles) {      // A / B switch of development runs (RGBD_RB_STATIC=1): tile = blockIdx.x + k * gridDim.x
+                    const int t = (int)blockIdx.x + drawn++ * (int)gridDim.x;
+                    return t < p.total_tiles ? t : p.total_tiles;
+                }
+                int t = atomicAdd(p.sched, 1);
+                if (t >= p.total_tiles) {
+                    // every CTA draws exactly one value past the end; the last of them re-arms the counter for the next
+                    // launch of this plan (stream order keeps that launch behind this one)
+                    if (t == p.total_tiles + (int)gridDim.x - 1) atomicExch(p.sched, 0);
+                    t = p.total_tiles;
+                }
+                return t;
+            };
+            int ahead = draw();
+            for (int k = 0;; ++k) {
+                const int tile = ahead;
+                const int q = k % kTileQ;
+                mbar_wait(tq_empty(q), (uint32_t)((k / kTileQ) & 1) ^ 1u);
+                tq_s[q] = tile;
+                mbar_arrive(tq_full(q));
+                if (tile >= p.total_tiles) break;
+                ahead = draw();
                 const RbTile tc = rb_tile(p, tile);
-                if (p.prefetch && tile + step < p.total_tiles) {
+                if (p.prefetch && ahead < p.total_tiles) {
                     // the next tile's pieces start their way HBM -> L2 now: the ring can hold only 4 of its 9+ pieces ahead of time
-                    const RbTile tn = rb_tile(p, tile + step);
+                    const RbTile tn = rb_tile(p, ahead);
                     for (int kb = 0; kb < p.kb1; ++kb)
                         for (int m = 0; m < 3; ++m) tma_prefetch_4d(&p.xmap, kb * kBlockK, tn.ox0 - 1, tn.oy0 - 1 + m * kRpm, tn.n);
                 }
@@ -186,11 +230,13 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
         }
     } else if (warp == 1) {
         // =========================== weight producer ===========================
-        if (lane == 0) {
+        {
             RingPos rw = {0, 0};
-            const bool tr = p.dbg != nullptr && blockIdx.x == 0;
+            const bool tr = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
             long long ww = 0;
-            for (int tile = first; tile < p.total_tiles; tile += step) {
+            for (int k = 0;; ++k) {
+                if (next_tile(k) >= p.total_tiles) break;      // whole warp; lane 0 issues the loads
+                if (lane != 0) continue;
                 for (int mk = 0; mk < 2 * p.kb1; ++mk, rw.next(kWStages)) {      // W1 twice: for halo M tiles 0 + 1, then for M tile 2
                     mbar_wait_t(w_empty(rw.s), rw.ph ^ 1u, tr, ww);
                     mbar_expect_tx(w_full(rw.s), (uint32_t)kWStageBytes);
@@ -224,7 +270,8 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
         const bool tr = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
         long long m_w1 = 0, m_x = 0, m_pre2 = 0, m_w2 = 0, m_t2 = 0, m_e3 = 0, m_w3 = 0;
         const long long m_begin = tr ? clock64() : 0;
-        for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
+        for (;; ++it) {
+            if (next_tile((int)it) >= p.total_tiles) break;
             // ---------------- P1 (D1[m] was drained by the epilogue of the previous tile: t1_ready waits below) ----------------
             // Both issuer warps wait for and release EVERY stage, also those whose MMAs the other warp issues: a parity wait is
             // only meaningful for a waiter that has seen the previous phase of the same barrier, so nobody may skip a stage
@@ -377,7 +424,9 @@ rb_fused_kernel(const __grid_constant__ RbParams p) {
         const bool tr = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
         long long e_d1 = 0, e_d2 = 0, e_d3 = 0, e_p1 = 0, e_p2 = 0, e_p3 = 0, e_res = 0, e_bw = 0, e_st = 0, e_top = 0;
         const long long e_begin = tr ? clock64() : 0;
-        for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
+        for (;; ++it) {
+            const int tile = next_tile((int)it);
+            if (tile >= p.total_tiles) break;
             const long long qt = tr ? clock64() : 0;
             const RbTile tc = rb_tile(p, tile);
             // this thread's output pixel (P3) and its residual row
@@ -533,6 +582,8 @@ extern "C" int rgbd_rb_plan_create(const rgbd_rb_desc *d, rgbd_rb_plan **out) {
     RGBD_CHECK_ARG((((uintptr_t)d->x | (uintptr_t)d->res | (uintptr_t)d->y | (uintptr_t)d->w1 | (uintptr_t)d->w2 | (uintptr_t)d->w3) & 15) == 0,
                    "base pointers must be 16-byte aligned");
     RGBD_CHECK_ARG((int64_t)d->N * d->H * d->W < 2147483647LL, "too many pixels");
+    RGBD_CHECK_ARG(d->sched_ws != nullptr && ((uintptr_t)d->sched_ws & 3) == 0,
+                   "sched_ws: the caller provides a zero-initialised int32 in device memory per plan (tile counter)");
     rgbd_rb_plan *pl = new (std::nothrow) rgbd_rb_plan();
     if (!pl) {
         rgbd_set_error("rb: out of host memory");
@@ -547,7 +598,9 @@ extern "C" int rgbd_rb_plan_create(const rgbd_rb_desc *d, rgbd_rb_plan **out) {
     p.kb1 = d->Cin / kBlockK;
     p.nblk3 = d->Cout / kNB3;
     p.final_relu = d->final_relu;
+    p.sched = reinterpret_cast<int32_t *>(d->sched_ws);
     p.prefetch = getenv("RGBD_RB_NOPREFETCH") == nullptr;
+    p.static_tiles = getenv("RGBD_RB_STATIC") != nullptr;
     p.wide_io = ((d->res_cstride | d->res_coff) & 15) == 0 && ((uintptr_t)d->res & 31) == 0;
     p.dbg = nullptr;
 #ifdef RGBD_TIMING_PROBES

@@ -1043,7 +1043,8 @@ class _DecompressHandle:
         # a valid stream is consumed exactly: the decoder ends on its last word (reads past the end return zeros and
         # would otherwise decode a truncated or foreign stream silently to garbage)
         pos = self.prog.io["state_host"].numpy()[:, 1]
-        if (pos != self.word_lens).any():
+        # (RGBD_RANS_SKIP: timing experiments of development builds that skip the coder kernels, profiles/tools/skip_probe.py)
+        if (pos != self.word_lens).any() and not os.environ.get("RGBD_RANS_SKIP"):
             bad = int(np.nonzero(pos != self.word_lens)[0][0])
             raise ValueError(f"corrupt stream {bad}: decoder stopped at word {int(pos[bad])} of {int(self.word_lens[bad])}")
         r, d = self.prog.io["out_r"], self.prog.io["out_d"]

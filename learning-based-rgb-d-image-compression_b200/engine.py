@@ -446,11 +446,7 @@ class Builder:
             d.cout_pad = 16 if ln.get("shuffle") else pc.cout_pad
             self.prog.keep.append(d)
             if use_tc:
-                if self._sched is None or self._sched_used == self._sched.numel():
-                    self._sched = self.raw((4096,), torch.int32, zero=True)
-                    self._sched_used = 0
-                d.sched_ws = self._sched.data_ptr() + 4 * self._sched_used
-                self._sched_used += 1
+                d.sched_ws = self._sched_slot()
                 d.w = pc.wtc.data_ptr()
                 if w_folded is not None:
                     d.w = w_folded.data_ptr()
@@ -517,6 +513,7 @@ class Builder:
         d.Cmid, d.Cout = 96, pc3.Cout
         d.res_cstride, d.res_coff, d.y_cstride, d.y_coff = res.cstride, res.coff, out.cstride, out.coff
         d.final_relu = int(bool(final_relu))
+        d.sched_ws = self._sched_slot()
         handle = C.c_void_p()
         L.check(L.load().rgbd_rb_plan_create(C.byref(d), C.byref(handle)), "rgbd_rb_plan_create")
         self.prog.rb_plans.append(handle)
@@ -562,6 +559,15 @@ class Builder:
         self.op("rgbd_se_gate", cache["partial"].data_ptr(), pstride, nchunk, x.N, HW, x.C, w1.data_ptr(), w2.data_ptr(),
                 Cr, int(plus_one), cache["work"].data_ptr(), scale.data_ptr())
         return scale
+
+    def _sched_slot(self):
+        """Address of a fresh zero-initialised int32: the tile counter of one persistent-kernel plan."""
+        if self._sched is None or self._sched_used == self._sched.numel():
+            self._sched = self.raw((4096,), torch.int32, zero=True)
+            self._sched_used = 0
+        ptr = self._sched.data_ptr() + 4 * self._sched_used
+        self._sched_used += 1
+        return ptr
 
     def se_cache(self, view):
         """Keep the SE partial sums of this buffer between se_scale() calls (see there)."""

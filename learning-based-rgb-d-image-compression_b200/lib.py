@@ -52,7 +52,7 @@ class RbDesc(C.Structure):
         ("Cin", C.c_int32), ("x_cstride", C.c_int32), ("x_coff", C.c_int32),
         ("Cmid", C.c_int32), ("Cout", C.c_int32),
         ("res_cstride", C.c_int32), ("res_coff", C.c_int32), ("y_cstride", C.c_int32), ("y_coff", C.c_int32),
-        ("final_relu", C.c_int32), ("_pad", C.c_int32),
+        ("final_relu", C.c_int32), ("_pad", C.c_int32), ("sched_ws", C.c_void_p),
     ]
 
 
