@@ -34,7 +34,26 @@ for model_name in ("ELIC_united", "ELIC_united_R2D", "my_ELIC_united_R2D_run"):
             net = cls(config=model_config(), channel=4).eval()
             picked[model_name] = [type(net).__module__, type(net).__name__, len(net.state_dict())]
             break
-print(json.dumps({"keys": keys, "picked": picked,
+# the reference's own Tester.get_net + restore (testing/tester.py:55-66,100-108) on our class: construct by substring lookup,
+# torch.load, load_state_dict, update(force=True), .to(device).  __init__ is bypassed only because it hard-codes
+# device = "cuda" and opens a dataset; get_net / restore run unmodified (this container has no GPU: device = "cpu").
+import tempfile, torch
+from testing.tester_united import TesterUnited
+from rgbd_b200.synthetic import synthetic_state_dict
+harness = {}
+with tempfile.TemporaryDirectory() as tmp:
+    seed = rgbd_b200.ELIC_united(config=model_config(), channel=4).eval()
+    seed.load_state_dict(synthetic_state_dict(seed, 0, "mid"))
+    seed.update(force=True)
+    ckpt = os.path.join(tmp, "checkpoint_best_loss.pth.tar")
+    torch.save({"state_dict": seed.state_dict(), "epoch": 7}, ckpt)
+    t = object.__new__(TesterUnited)
+    t.device, t.channel, t.ckpt_dir_path = "cpu", 4, tmp
+    epoch = t.get_net(model_config=model_config(), model_name="ELIC_united", ckpt_path=None)   # finds the file in ckpt_dir_path
+    same = all(torch.equal(a, b) for a, b in zip(t.net.state_dict().values(), seed.state_dict().values()))
+    harness = {"epoch": int(epoch), "cls": [type(t.net).__module__, type(t.net).__name__], "state_equal": bool(same),
+               "cdf_rows": int(t.net.rgb_gaussian_conditional.quantized_cdf.shape[0]), "training": bool(t.net.training)}
+print(json.dumps({"keys": keys, "picked": picked, "harness": harness,
                   "ours": [rgbd_b200.ELIC_united.__module__, rgbd_b200.ELIC_united_R2D.__module__]}))
 '''
 
@@ -56,3 +75,6 @@ def test_dropin_patches_the_reference_model_zoo(golden_dir):
         mod, name, nkeys = info["picked"][model_name]
         assert name == cls_name and mod in info["ours"], (model_name, mod, name)   # OUR class, not the reference's
         assert nkeys == want_keys[cls_name]
+    h = info["harness"]      # the reference's Tester.get_net / restore ran on our class
+    assert h["epoch"] == 7 and h["cls"][1] == "ELIC_united" and h["cls"][0] in info["ours"]
+    assert h["state_equal"] and h["cdf_rows"] == 64 and not h["training"]
