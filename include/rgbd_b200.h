@@ -41,6 +41,7 @@ extern "C" {
 #define RGBD_ACT_NONE 0
 #define RGBD_ACT_RELU 1
 #define RGBD_ACT_LEAKY 2 /* negative slope 0.01 (nn.LeakyReLU default) */
+#define RGBD_ACT_GELU 3  /* exact GELU, 0.5 v (1 + erf(v / sqrt 2)) (nn.GELU default; the Swin MLPs of STF_united) */
 
 /* epilogue modes of the conv kernels; v = acc + bias */
 #define RGBD_EPI_LINEAR 0   /* y = act(v + res)                  res optional            */
@@ -200,6 +201,27 @@ int rgbd_copy_view(const void *x, void *y, int32_t dtype, int64_t npix, int32_t 
 int rgbd_cast_view_bf16(const float *x, void *y, int64_t npix, int32_t C, int32_t x_cstride, int32_t x_coff,
                         int32_t y_cstride, int32_t y_coff, void *stream);
 int rgbd_zero(void *p, int64_t bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Token-side ops of SymmetricalTransFormerUnited (models/stf_united.py); tokens = pixels of NHWC views, the Linear layers
+ * run as 1x1 convs (rgbd_conv_*).
+ * ------------------------------------------------------------------------------------------ */
+/* nn.LayerNorm over the C channels of every pixel (biased variance, eps inside the root; stf_united.py:157,193).  With
+ * gather2x2 the token is PatchMerging's concatenation [x(2i,2j) | x(2i+1,2j) | x(2i,2j+1) | x(2i+1,2j+1)] of four pixels of
+ * C / 4 channels of the [N, Hin, Win] input (stf_united.py:236-244) and npix = N * Hin/2 * Win/2.  C <= 768. */
+int rgbd_layernorm(const void *x, int32_t x_dtype, void *y, int32_t y_dtype, int64_t npix, int32_t C, int32_t x_cstride,
+                   int32_t x_coff, int32_t y_cstride, int32_t y_coff, const float *gamma, const float *beta, float eps,
+                   int32_t gather2x2, int32_t Hin, int32_t Win, void *stream);
+/* nn.PixelShuffle(2) on NHWC: y[n, 2h+i, 2w+j, c] = x[n, h, w, 4c + 2i + j] (PatchSplit :270-273, end convs :574-582). */
+int rgbd_pixel_shuffle2(const void *x, void *y, int32_t dtype, int32_t N, int32_t H, int32_t W, int32_t Cout, int32_t x_cstride,
+                        int32_t x_coff, int32_t y_cstride, int32_t y_coff, void *stream);
+/* (Shifted-)window multi-head attention (WindowAttention.forward :83-115 inside SwinTransformerBlock.forward :162-212):
+ * qkv holds [q | k | v] (C channels each, head-major) per pixel; windows of window x window tokens on the map rolled by
+ * -shift; scores q k^T * scale + relative-position bias (bias_table [(2 window - 1)^2][heads], fp32) + the -100 mask between
+ * the regions of BasicLayer.forward :334-352 when shift > 0; softmax; times v; written back at the unrolled position. */
+int rgbd_window_attention(const void *qkv, void *out, int32_t dtype, int32_t N, int32_t H, int32_t W, int32_t C, int32_t heads,
+                          int32_t window, int32_t shift, const float *bias_table, float scale, int32_t qkv_cstride,
+                          int32_t qkv_coff, int32_t out_cstride, int32_t out_coff, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Metrics and image export next to the path (testing/tester_united.py:92-123, utils/metrics.py:8-14).

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librgbd_b200.so")
-SOURCES = ["runtime.cu", "rans.cu", "entropy.cu", "aux.cu", "conv_simt.cu", "conv_halo.cu", "conv_rb.cu", "metrics.cu", "host_tables.cpp"]
+SOURCES = ["runtime.cu", "rans.cu", "entropy.cu", "aux.cu", "conv_simt.cu", "conv_halo.cu", "conv_rb.cu", "metrics.cu", "swin.cu", "host_tables.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -532,8 +532,13 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] += r[i];
                         }
+                        if (d.act == RGBD_ACT_GELU) {      // exact GELU (the Swin MLPs): a uniform branch, off the hot layers' path
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = act_fn(v[i], slope);
+                            for (int i = 0; i < 16; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = act_fn(v[i], slope);
+                        }
                     } else {  // RGBD_EPI_BILERP
                         const int64_t rbase = (int64_t)tc.n * d.res_H * d.res_W;
                         const int cc = d.res_coff + co;

@@ -44,6 +44,7 @@ template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bf
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == RGBD_ACT_RELU) return v > 0.f ? v : 0.f;
     if (act == RGBD_ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
+    if (act == RGBD_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
     return v;
 }
 

@@ -25,6 +25,7 @@ def install(reference_root, compressai_root=None):
     models.modelZoo["ELIC_united_R2D"] = rgbd_b200.ELIC_united_R2D
     models.modelZoo["ELIC_united"] = rgbd_b200.ELIC_united
     models.modelZoo["ELIC"] = rgbd_b200.ELIC            # single-modality baselines (testing/tester_single.py)
+    models.modelZoo["STF_united"] = rgbd_b200.SymmetricalTransFormerUnited
     return models.modelZoo
 
 

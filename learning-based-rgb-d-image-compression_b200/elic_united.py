@@ -269,8 +269,9 @@ class ELIC_united(nn.Module):
         b.release(a, t)
         return y
 
-    def _esa(self, b, m, x, out):
-        """ESA (attention.py:70-97): x * sigmoid(conv4(upsample(small path) + conv_f(conv1 x)))"""
+    def _esa(self, b, m, x, out, res=None):
+        """ESA (attention.py:70-97): x * sigmoid(conv4(upsample(small path) + conv_f(conv1 x))) (+ res: the residual
+        fusion of STF_united, stf_united.py:494-497)"""
         c1_ = b.conv(self._pc(m.conv1), x)
         c1 = b.conv(self._pc(m.conv2), c1_)
         vmax = b.maxpool7s3(c1)
@@ -283,11 +284,11 @@ class ELIC_united(nn.Module):
         b.release(c3)
         s = b.conv(self._pc(m.conv_f), c1_, epi=L.EPI_BILERP, res=c3b)
         b.release(c1_, c3b)
-        y = b.conv(self._pc(m.conv4), s, out=out, epi=L.EPI_GATE, mul=x)
+        y = b.conv(self._pc(m.conv4), s, out=out, epi=L.EPI_GATE, mul=x, res=res)
         b.release(s)
         return y
 
-    def _bispf(self, b, m, rgb, depth, rgb_out, depth_out):
+    def _bispf(self, b, m, rgb, depth, rgb_out, depth_out, res_r=None, res_d=None):
         """bi_spf / bi_spf_single (attention.py:14-48). rgb/depth: N-channel views; *_out: the
         N-channel slot after them in the 2N-wide concat buffer (rgb_out None for the single form)."""
         Nh = m.r_ext.out_channels
@@ -295,8 +296,8 @@ class ELIC_united(nn.Module):
         b.conv(self._pc(m.r_ext), rgb, out=e.sub(0, Nh), act=RELU, y2=e.sub(2 * Nh, Nh))
         b.conv(self._pc(m.d_ext), depth, out=e.sub(Nh, Nh), act=RELU)
         if rgb_out is not None:
-            self._esa(b, m.r_esa, e.sub(0, 2 * Nh), rgb_out)       # ESA(cat(r, d))
-        self._esa(b, m.d_esa, e.sub(Nh, 2 * Nh), depth_out)        # ESA(cat(d, r))
+            self._esa(b, m.r_esa, e.sub(0, 2 * Nh), rgb_out, res=res_r)       # ESA(cat(r, d))
+        self._esa(b, m.d_esa, e.sub(Nh, 2 * Nh), depth_out, res=res_d)        # ESA(cat(d, r))
         b.release(e)
 
     def _transform(self, b, rgb_seq, depth_seq, r, d, final_dtype=None):
@@ -561,8 +562,8 @@ class ELIC_united(nn.Module):
         sublen = c * h * (w // 2)
         return ny // sublen, sublen
 
-    def _common_front(self, b, B, H, W):
-        """image -> g_a -> h_a. Returns io views."""
+    def _analysis(self, b, B, H, W):
+        """images -> g_a.  Registers the fp32 NCHW input buffers in the program and returns the latents (fp32 views)."""
         p = b.prog
         # bf16 tensor-core mode: the images enter as a two-term bf16 expansion [hi | lo | hi] so the first
         # layer keeps fp32-like accuracy (16-bit depth is represented exactly) at no extra MMA cost
@@ -578,8 +579,16 @@ class ELIC_united(nn.Module):
         b.op("rgbd_nchw_to_nhwc", in_r.data_ptr(), x_r.ptr(), _DT[x_r.dtype], B, 3, H, W, x_r.cstride, x_r.coff, split)
         b.op("rgbd_nchw_to_nhwc", in_d.data_ptr(), x_d.ptr(), _DT[x_d.dtype], B, 1, H, W, x_d.cstride, x_d.coff, split)
         b.stage = "g_a"
-        y_r, y_d = self._transform(b, self.g_a.rgb_analysis_transform, self.g_a.depth_analysis_transform,
-                                   x_r, x_d, final_dtype=torch.float32)
+        return self._transform(b, self.g_a.rgb_analysis_transform, self.g_a.depth_analysis_transform, x_r, x_d,
+                               final_dtype=torch.float32)
+
+    def _synthesis(self, b, yhat_r, yhat_d):
+        """y_hat -> g_s: the reconstructions as NHWC views (3 and 1 channels)."""
+        return self._transform(b, self.g_s.rgb_synthesis_transform, self.g_s.depth_synthesis_transform, yhat_r, yhat_d)
+
+    def _common_front(self, b, B, H, W):
+        """image -> g_a -> h_a. Returns io views."""
+        y_r, y_d = self._analysis(b, B, H, W)
         b.stage = "h_a"
         z_r, z_d = self._h_a(b, y_r, y_d)
         b.stage = "coder"
@@ -755,8 +764,7 @@ class ELIC_united(nn.Module):
 
         self._context_chain(b, ctx, ctx_rgb, yhat["r"], yhat["d"], code_step)
         b.stage = "g_s"
-        x_r, x_d = self._transform(b, self.g_s.rgb_synthesis_transform, self.g_s.depth_synthesis_transform,
-                                   yhat["r"], yhat["d"])
+        x_r, x_d = self._synthesis(b, yhat["r"], yhat["d"])
         b.stage = "io"
         out_r = b.raw((B, 3, H, W), torch.float32)
         out_d = b.raw((B, 1, H, W), torch.float32)
@@ -806,8 +814,7 @@ class ELIC_united(nn.Module):
 
         self._context_chain(b, ctx, ctx_rgb, yhat["r"], yhat["d"], code_step)
         b.stage = "g_s"
-        x_r, x_d = self._transform(b, self.g_s.rgb_synthesis_transform, self.g_s.depth_synthesis_transform,
-                                   yhat["r"], yhat["d"])
+        x_r, x_d = self._synthesis(b, yhat["r"], yhat["d"])
         b.stage = "io"
         out_r = b.raw((B, 3, H, W), torch.float32)
         out_d = b.raw((B, 1, H, W), torch.float32)

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librgbd_b200.so")
 
 DT_F32, DT_BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU = 0, 1, 2, 3
 EPI_LINEAR, EPI_GATE, EPI_BILERP, EPI_SHUFFLE2 = 0, 1, 2, 3
 MAX_TAPS = 25
 
@@ -99,6 +99,9 @@ _PROTOS = {
     "rgbd_rans_decode_chunk": [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i32, C.POINTER(RansTables), _vp],
     "rgbd_rans_decode_streams": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i32,
                                  C.POINTER(RansTables), _vp],
+    "rgbd_layernorm": [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _i32, _i32, _i32, _vp],
+    "rgbd_pixel_shuffle2": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "rgbd_window_attention": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _f32, _i32, _i32, _i32, _i32, _vp],
     "rgbd_sq_error_sums": [_vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp],
     "rgbd_ssim_level": [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp],
     "rgbd_avgpool2": [_vp, _vp, _i32, _i32, _i32, _i32, _vp],

@@ -74,6 +74,12 @@ def synthetic_state_dict(model, seed=0, preset="mid"):
                 v = v * 0.5     # residual branches: keep the sum's variance from growing too fast
         elif leaf == "weight" and len(shape) == 2:
             v = torch.randn(shape, generator=g, device="cpu") * math.sqrt(1.0 / shape[1])
+        elif leaf == "weight" and len(shape) == 1:
+            # LayerNorm gains (the Swin blocks of STF_united): near one, deterministic
+            v = 1.0 + (torch.rand(shape, generator=g, device="cpu") - 0.5) * 0.2
+        elif leaf == "relative_position_bias_table":
+            # the reference initialises it from the global RNG (trunc_normal_, std 0.02): make it a function of the key
+            v = torch.randn(shape, generator=g, device="cpu") * 0.2
         elif leaf == "bias":
             v = (torch.rand(shape, generator=g, device="cpu") - 0.5) * 0.1
         else:

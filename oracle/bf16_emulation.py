@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from .elic_oracle import ElicOracle
 from .model_oracle import OracleCodec
+from .stf_oracle import StfOracle
 
 
 def _bf(t):
@@ -33,3 +34,15 @@ class Bf16OracleCodec(_Bf16Convs, OracleCodec):
 
 class Bf16ElicOracle(_Bf16Convs, ElicOracle):
     pass
+
+
+class Bf16StfOracle(_Bf16Convs, StfOracle):
+    """+ every nn.Linear of the Swin blocks as a bf16 GEMM, and the tensors the CUDA path stores between launches
+    (LayerNorm outputs, attention outputs) rounded to bf16."""
+
+    def _lin(self, p, x):
+        w, bias = self.sd[p + ".weight"], self.sd.get(p + ".bias")
+        return _bf(F.linear(_bf(x), _bf(w), bias))
+
+    def _ln(self, p, x):
+        return _bf(super()._ln(p, x))

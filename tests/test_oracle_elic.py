@@ -47,4 +47,4 @@ def test_elic_state_dict_keys_match_reference(golden_dir):
         got = {k: list(v.shape) for k, v in net.state_dict().items()}
         assert list(got) == list(want), name
         assert got == want, name
-    assert list(rgbd_b200.modelZoo) == ["ELIC_united_R2D", "ELIC_united", "ELIC"]   # substring lookup order
+    assert list(rgbd_b200.modelZoo) == ["ELIC_united_R2D", "ELIC_united", "ELIC", "STF_united"]   # substring lookup order (models/__init__.py:11-20)
