@@ -47,7 +47,7 @@ constexpr int kMinSmem = 120 * 1024;               // > half an SM: never two of
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMaxGroups = 4;
 constexpr int kTileQ = 4;                          // depth of the CTA's tile queue (dynamic scheduler)
-constexpr int kMaxBias = 1024;
+constexpr int kMaxBias = 2048;                   // widest layer: the Swin MLP of STF_united, 384 -> 1536
 
 struct HParams {
     CUtensorMap amap[4];

@@ -580,7 +580,9 @@ class Builder:
             cache["valid"] = _subtract(cache["valid"], view.coff, view.coff + view.C)
 
     def maxpool7s3(self, x):
-        assert x.coff == 0 and x.C == x.cstride
+        # dense buffers; a bf16 buffer whose channel count was padded to a multiple of 8 (f = 12 in STF_united's narrowest
+        # ESA) is pooled over its padded width — the padding lanes are never read as channels by anyone
         out = self.alloc(x.N, (x.H - 7) // 3 + 1, (x.W - 7) // 3 + 1, x.C, x.dtype)
-        self.op("rgbd_maxpool7s3", x.ptr(), out.ptr(), _DT[x.dtype], x.N, x.H, x.W, x.C)
+        assert x.coff == 0 and out.cstride == x.cstride and x.cstride - x.C < 8
+        self.op("rgbd_maxpool7s3", x.ptr(), out.ptr(), _DT[x.dtype], x.N, x.H, x.W, x.cstride)
         return out

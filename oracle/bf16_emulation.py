@@ -37,8 +37,8 @@ class Bf16ElicOracle(_Bf16Convs, ElicOracle):
 
 
 class Bf16StfOracle(_Bf16Convs, StfOracle):
-    """+ every nn.Linear of the Swin blocks as a bf16 GEMM, and the tensors the CUDA path stores between launches
-    (LayerNorm outputs, attention outputs) rounded to bf16."""
+    """+ every nn.Linear of the Swin blocks as a bf16 GEMM, and the tensors a bf16 path stores between launches
+    (LayerNorm outputs, the residual stream) rounded to bf16."""
 
     def _lin(self, p, x):
         w, bias = self.sd[p + ".weight"], self.sd.get(p + ".bias")
@@ -46,3 +46,7 @@ class Bf16StfOracle(_Bf16Convs, StfOracle):
 
     def _ln(self, p, x):
         return _bf(super()._ln(p, x))
+
+    @staticmethod
+    def _add(a, b):
+        return _bf(a + b)          # the residual stream lives in bf16 between launches

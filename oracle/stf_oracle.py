@@ -32,6 +32,11 @@ class StfOracle(OracleCodec):
         return F.linear(x, self.sd[p + ".weight"], self.sd.get(p + ".bias"))
 
     @staticmethod
+    def _add(a, b):
+        """the residual adds (a hook: oracle/bf16_emulation.py rounds the sum, as a bf16 residual stream does)"""
+        return a + b
+
+    @staticmethod
     def _windows(x, ws):
         B, H, W, C = x.shape
         return x.view(B, H // ws, ws, W // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, C)
@@ -75,9 +80,9 @@ class StfOracle(OracleCodec):
         o = self._unwindows(self._lin(p + ".attn.proj", o), ws, B, H, W)
         if shift:
             o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
-        x = x + o
+        x = self._add(x, o)
         h = F.gelu(self._lin(p + ".mlp.fc1", self._ln(p + ".norm2", x)))
-        return x + self._lin(p + ".mlp.fc2", h)
+        return self._add(x, self._lin(p + ".mlp.fc2", h))
 
     def _layer(self, p, x, depth, heads, down):
         for i in range(depth):
@@ -94,7 +99,7 @@ class StfOracle(OracleCodec):
         """rgb_y + rgb_f, depth_y + depth_f around a bi_spf on NCHW views (stf_united.py:492-497)."""
         rc, dc = r.permute(0, 3, 1, 2).contiguous(), d.permute(0, 3, 1, 2).contiguous()
         rf, df = self._spf(p, rc, dc)
-        return (rc + rf).permute(0, 2, 3, 1).contiguous(), (dc + df).permute(0, 2, 3, 1).contiguous()
+        return self._add(rc, rf).permute(0, 2, 3, 1).contiguous(), self._add(dc, df).permute(0, 2, 3, 1).contiguous()
 
     # ------------------------------------------------------------ transforms
     def g_a(self, rgb, depth):

@@ -38,10 +38,10 @@ def test_layernorm_and_patch_merging_gather():
     g = torch.Generator().manual_seed(1)
     x = torch.randn(2, 6, 10, 48 + 8, generator=g) * 3 + 1
     gamma, beta = torch.rand(48, generator=g) + 0.5, torch.randn(48, generator=g)
-    xd = x.to(DEV)
+    xd, gd, bd = x.to(DEV), gamma.to(DEV), beta.to(DEV)        # (named: a temporary would be freed before the launch)
     y = torch.zeros(2, 6, 10, 64, device=DEV)
-    L.call("rgbd_layernorm", xd.data_ptr(), L.DT_F32, y.data_ptr(), L.DT_F32, 2 * 6 * 10, 48, 56, 8, 64, 16, gamma.to(DEV).data_ptr(),
-           beta.to(DEV).data_ptr(), 1e-5, 0, 6, 10, sp())
+    L.call("rgbd_layernorm", xd.data_ptr(), L.DT_F32, y.data_ptr(), L.DT_F32, 2 * 6 * 10, 48, 56, 8, 64, 16, gd.data_ptr(),
+           bd.data_ptr(), 1e-5, 0, 6, 10, sp())
     want = F.layer_norm(x[..., 8:], (48,), gamma, beta, 1e-5)
     assert torch.allclose(y[..., 16:].cpu(), want, atol=2e-5) and float(y[..., :16].abs().max()) == 0
     # PatchMerging: [x(2i,2j) | x(2i+1,2j) | x(2i,2j+1) | x(2i+1,2j+1)] then LayerNorm(4C)
@@ -49,15 +49,17 @@ def test_layernorm_and_patch_merging_gather():
     xm = x[..., 8:]
     cat = torch.cat([xm[:, 0::2, 0::2], xm[:, 1::2, 0::2], xm[:, 0::2, 1::2], xm[:, 1::2, 1::2]], -1)
     ym = torch.zeros(2, 3, 5, 192, device=DEV, dtype=torch.bfloat16)
-    L.call("rgbd_layernorm", xd.data_ptr(), L.DT_F32, ym.data_ptr(), L.DT_BF16, 2 * 3 * 5, 192, 56, 8, 192, 0, g4.to(DEV).data_ptr(),
-           b4.to(DEV).data_ptr(), 1e-5, 1, 6, 10, sp())
+    g4d, b4d = g4.to(DEV), b4.to(DEV)
+    L.call("rgbd_layernorm", xd.data_ptr(), L.DT_F32, ym.data_ptr(), L.DT_BF16, 2 * 3 * 5, 192, 56, 8, 192, 0, g4d.data_ptr(),
+           b4d.data_ptr(), 1e-5, 1, 6, 10, sp())
     assert rel_err(ym.float().cpu(), F.layer_norm(cat, (192,), g4, b4, 1e-5)) < 6e-3        # one bf16 rounding
 
 
 def test_pixel_shuffle_matches_torch():
     x = torch.randn(2, 5, 7, 4 * 24)
     y = torch.zeros(2, 10, 14, 24, device=DEV)
-    L.call("rgbd_pixel_shuffle2", x.to(DEV).data_ptr(), y.data_ptr(), L.DT_F32, 2, 5, 7, 24, 96, 0, 24, 0, sp())
+    xd = x.to(DEV)
+    L.call("rgbd_pixel_shuffle2", xd.data_ptr(), y.data_ptr(), L.DT_F32, 2, 5, 7, 24, 96, 0, 24, 0, sp())
     want = F.pixel_shuffle(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
     assert torch.equal(y.cpu(), want)
 
@@ -71,8 +73,9 @@ def test_window_attention_matches_reference_arithmetic(shift):
     qkv = torch.randn(B, H, W, 3 * Cc, generator=g)
     table = torch.randn((2 * ws - 1) ** 2, heads, generator=g) * 0.5
     out = torch.zeros(B, H, W, Cc, device=DEV)
-    L.call("rgbd_window_attention", qkv.to(DEV).data_ptr(), out.data_ptr(), L.DT_F32, B, H, W, Cc, heads, ws, shift,
-           table.to(DEV).data_ptr(), float((Cc // heads) ** -0.5), 3 * Cc, 0, Cc, 0, sp())
+    qd, td = qkv.to(DEV), table.to(DEV)
+    L.call("rgbd_window_attention", qd.data_ptr(), out.data_ptr(), L.DT_F32, B, H, W, Cc, heads, ws, shift,
+           td.data_ptr(), float((Cc // heads) ** -0.5), 3 * Cc, 0, Cc, 0, sp())
     # reference arithmetic on the CPU
     from rgbd_b200.modules_stf import WindowAttention
     idx = WindowAttention(Cc, ws, heads).relative_position_index.view(-1)
