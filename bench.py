@@ -24,7 +24,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 UNIT = "pairs/s"
-MODELS = {"ELIC_united": True, "ELIC_united_R2D": False}      # name -> bidirectional (OracleCodec cross)
+MODELS = {"ELIC_united": True, "ELIC_united_R2D": False, "STF_united": True}      # name -> bidirectional (OracleCodec cross)
+
+
+def make_oracle(model, sd, use_ref_coder=False, bf16=False):
+    """The CPU restatement of `model` over the state_dict `sd` (bf16: the bf16-arithmetic emulation of the parity gate)."""
+    if model == "STF_united":
+        from oracle.bf16_emulation import Bf16StfOracle
+        from oracle.stf_oracle import StfOracle
+        return (Bf16StfOracle if bf16 else StfOracle)(sd, use_ref_coder=use_ref_coder)
+    from oracle.bf16_emulation import Bf16OracleCodec
+    from oracle.model_oracle import OracleCodec
+    return (Bf16OracleCodec if bf16 else OracleCodec)(sd, cross=MODELS[model], use_ref_coder=use_ref_coder)
 
 
 def metric_name(args):
@@ -156,7 +167,6 @@ def cpu_arm(args, pairs, steps, warmup, trace=False):
     oracle/tables.py."""
     import torch
     import rgbd_b200
-    from oracle.model_oracle import OracleCodec
     from oracle.ref_loader import ref_ext_available
     from oracle.tables import updated_state_dict
     cores = os.cpu_count() or 1
@@ -164,7 +174,7 @@ def cpu_arm(args, pairs, steps, warmup, trace=False):
     net = getattr(rgbd_b200, args.model)(config=rgbd_b200.model_config(), channel=4).eval()   # key / shape holder only
     sd = updated_state_dict(rgbd_b200.synthetic.synthetic_state_dict(net, 0, args.preset))
     use_ref = ref_ext_available()
-    orc = OracleCodec(sd, cross=MODELS[args.model], use_ref_coder=use_ref)
+    orc = make_oracle(args.model, sd, use_ref_coder=use_ref)
     rgb, depth = make_inputs(pairs, args.height, args.width, seed=1234, depth_div=depth_div(args))
     times = []
     sample = []      # per pair: stream bytes, symbols and reconstruction of the CPU path (the parity reference of the GPU line)
@@ -548,8 +558,7 @@ def parity_gate(net, args, coded, dev, orc):
         gs = dict(zip(("r", "d"), orc.g_s(*yh)))
         pre = {k: nchw(dec.io["x_nhwc"][k]) for k in ("r", "d")}       # before decompress()'s clamp to [0, 1]
         if i == 0 and net.precision == "bf16":                         # what bf16 arithmetic itself costs on these weights
-            from oracle.bf16_emulation import Bf16OracleCodec
-            for m, e in zip(("r", "d"), Bf16OracleCodec(orc.sd, cross=orc.cross).g_s(*yh)):
+            for m, e in zip(("r", "d"), make_oracle(args.model, orc.sd, bf16=True).g_s(*yh)):
                 emu_db.append(10 * math.log10(16.0 * float(gs[m].double().var()) / max(1e-30, float(((e.double() - gs[m].double()) ** 2).mean()))))
         for key, m, x in (("r_strings", "r", rgb), ("d_strings", "d", depth)):
             nbytes = sum(len(s_) for grp in c[key] for s_ in grp)
