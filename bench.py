@@ -320,8 +320,10 @@ def run_b200(args):
         W_ = max(3, args.warmup)
         if os.environ.get("RGBD_BENCH_FAKE_OOM") and B == int(os.environ["RGBD_BENCH_FAKE_OOM"]):
             raise torch.OutOfMemoryError("fake OOM (test hook)")
-        steps_device(W_)
-        steps_e2e(1)
+        # every slot's launch plans (and CUDA graphs) must exist before the timed region: with few jobs per step (strong
+        # scaling at many GPUs: one job per rank) W_ steps would not reach the higher slots
+        steps_device(max(W_, -(-max(S, D) // J)))
+        steps_e2e(max(1, -(-max(S, D) // J)))
         import types
         return types.SimpleNamespace(**{k: v for k, v in locals().items() if k != "types"})
 
