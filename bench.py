@@ -470,6 +470,10 @@ def run_b200(args):
         }
     # ---- untimed extras on rank 0: free the pipeline's plans, then batch-1 latency and the parity gate
     del ns, pipe, steps_device, steps_e2e, res, res2
+    if world > 1:
+        # the CPU baseline, the parity gate and the batch-1 latency belong to the N = 1 line only (the other ranks would sit in
+        # a barrier meanwhile; measured at N = 8: the CPU path ran 35x slower beside seven spinning ranks)
+        args.no_cpu_baseline = args.no_latency = True
     if rank == 0 and not (args.no_latency and args.no_cpu_baseline):
         net._invalidate()
         import gc
@@ -484,6 +488,7 @@ def run_b200(args):
             line["cpu_baseline"] = cb
             line["parity_vs_cpu_path"] = parity_gate(net, args, coded, dev, orc)
     if rank == 0:
+        line.setdefault("cpu_baseline", None)      # (N = 1 only, see above)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
