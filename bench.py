@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--model", default="ELIC_united", choices=sorted(MODELS))
     ap.add_argument("--batch", type=int, default=0, help="pairs per job (default: as many as fit the HBM budget)")
     ap.add_argument("--precision", default=os.environ.get("RGBD_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--slots", type=int, default=5, help="jobs in flight per GPU (own launch plan + CUDA stream each)")
+    ap.add_argument("--slots", type=int, default=4, help="jobs in flight per GPU (own launch plan + CUDA stream each)")
     ap.add_argument("--jobs-per-step", type=int, default=0, help="jobs of --batch pairs per GPU and step (default: --slots)")
     ap.add_argument("--total-pairs", type=int, default=0,
                     help="strong scaling (BASELINE configs[2]): this many pairs per step in total, sharded "
@@ -334,8 +334,9 @@ def run_b200(args):
     elif args.precision == "fp32":
         candidates = [2, 1]
     else:
-        # measured on B200 (profiles/README.md, round 2): at the same HBM footprint, 5 + 5 plans of 40 pairs beat 8 + 8 of 24
-        # (the 32x40 context-model launches fill the GPU better); jobs beyond 48 pairs gain nothing more
+        # measured on B200 (profiles/README.md, round 2, one box): at the same HBM footprint 4 + 4 plans of 48 pairs (337 / 347 e2e
+        # pairs/s, conv roofline 0.50) >= 5 + 5 of 40 (326 / 346, 0.49) >= 6 + 6 of 32 (327 / 329, 0.49) > 10 + 10 of 20 (318 / 304,
+        # 0.45): the 32x40 context-model launches fill the GPU better the bigger the job
         b0 = 24 * (512 * 640) / (Hp * Wp) * 16 / (S + D)
         b0 = max(1, min(48, int(round(b0 / 4) * 4) if b0 >= 16 else int(b0)))
         if own is not None:
