@@ -299,3 +299,33 @@ def test_se_cache_range_bookkeeping():
             qhi = rng.randrange(qlo + 1, 65)
             miss = _missing(ranges, qlo, qhi)
             assert [any(a <= c < b for a, b in miss) for c in range(64)] == [qlo <= c < qhi and not truth[c] for c in range(64)]
+
+
+def test_concat_packing_of_skip_and_last_conv_equals_their_sum():
+    """ELIC_united._pc_concat: one 1x1 conv over [x | t2] with weights [W_skip | W3] and summed biases == skip(x) + conv3(t2)
+    (the widening ResidualBottleneck's last two launches as one)."""
+    torch.manual_seed(3)
+    net = rgbd_b200.ELIC_united(config=rgbd_b200.model_config(), channel=4)
+    skip, last = nn.Conv2d(24, 16, 1), nn.Conv2d(8, 16, 1)
+    pc = net._pc_concat(skip, last)
+    assert pc.Cin == 32 and pc.Cout == 16 and pc.k == 1
+    x, t2 = torch.randn(2, 24, 5, 7), torch.randn(2, 8, 5, 7)
+    want = skip(x) + last(t2)
+    w = pc.w32[0, :, :16]                                   # [Cin, Cout] of the single tap
+    got = torch.einsum("nchw,co->nohw", torch.cat([x, t2], 1), w) + pc.bias.view(1, -1, 1, 1)
+    assert torch.allclose(got, want, atol=1e-5)
+    assert net._pc_concat(skip, last) is pc                 # cached per pair of modules
+
+
+def test_linear_packing_for_the_token_layers_equals_torch():
+    """STF_united._pc_linear: an nn.Linear over tokens == the 1x1 conv the launch plan runs over the pixels."""
+    torch.manual_seed(4)
+    net = rgbd_b200.STF_united(config=rgbd_b200.model_config(), channel=4)
+    for lin in (nn.Linear(48, 144), nn.Linear(96, 48, bias=False)):
+        pc = net._pc_linear(lin)
+        assert (pc.Cin, pc.Cout, pc.k, pc.stride, pc.pad) == (lin.in_features, lin.out_features, 1, 1, 0)
+        tok = torch.randn(3, 10, lin.in_features)
+        got = tok @ pc.w32[0, :, :lin.out_features] + (pc.bias if pc.bias is not None else 0)
+        assert torch.allclose(got, lin(tok), atol=1e-5)
+    blk = net.g_a.rgb_ana_layers[0].blocks[1]
+    assert blk.shift_size == 2 and blk.window_size == 4 and blk.num_heads == 3 and abs(blk.attn.scale - 16 ** -0.5) < 1e-12
