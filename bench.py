@@ -598,7 +598,9 @@ def conv_roofline(net, B, Hp, Wp, dev, dec_slot=0):
     pk, _ = peaks()
     ridge = pk["bf16_tflops_sustained"] * 1e12 / (pk["hbm_gbs"] * 1e9)     # flop per byte
     total_ms, total_flops, n = 0.0, 0.0, 0
-    cls = {"tensor": [0.0, 0.0, 0.0, 0], "hbm": [0.0, 0.0, 0.0, 0]}       # ms, flops, bytes, launches
+    # ms, flops, bytes, launches per roof: arithmetic intensity > 1.1 x the ridge -> tensor, < 0.9 x -> hbm, else "ridge" (the fused
+    # bottleneck blocks: 208 flop/byte against a ridge of 210 — both roofs bound them equally)
+    cls = {"tensor": [0.0, 0.0, 0.0, 0], "ridge": [0.0, 0.0, 0.0, 0], "hbm": [0.0, 0.0, 0.0, 0]}
     stages = {}                                                             # stage -> [conv ms, conv flops, conv launches, other ms, other launches]
     progs = (net._program("encoder", B, Hp, Wp),
              net._program("decoder", B, Hp // 64, Wp // 64, slot=dec_slot))   # plans the timed run used: their buffers hold real streams
@@ -624,7 +626,8 @@ def conv_roofline(net, B, Hp, Wp, dev, dec_slot=0):
                 st[0] += ms
                 st[1] += op.flops
                 st[2] += 1
-                c = cls["tensor" if op.flops / max(1, op.bytes) >= ridge else "hbm"]
+                ai = op.flops / max(1, op.bytes)
+                c = cls["tensor" if ai > 1.1 * ridge else ("hbm" if ai < 0.9 * ridge else "ridge")]
                 c[0] += ms
                 c[1] += op.flops
                 c[2] += op.bytes
@@ -664,6 +667,13 @@ def conv_roofline(net, B, Hp, Wp, dev, dec_slot=0):
         "tensor_bound_launches": {"launches": cls["tensor"][3], "ms": round(cls["tensor"][0], 3),
                                   "tflops": round(cls["tensor"][1] / max(1e-9, cls["tensor"][0]) / 1e9, 1),
                                   "frac_of_bf16_peak": round(cls["tensor"][1] / max(1e-9, cls["tensor"][0]) / 1e9 / peak, 3)},
+        "ridge_launches": {"launches": cls["ridge"][3], "ms": round(cls["ridge"][0], 3),
+                           "tflops": round(cls["ridge"][1] / max(1e-9, cls["ridge"][0]) / 1e9, 1),
+                           "frac_of_bf16_peak": round(cls["ridge"][1] / max(1e-9, cls["ridge"][0]) / 1e9 / peak, 3),
+                           "gbs": round(cls["ridge"][2] / max(1e-9, cls["ridge"][0]) / 1e6, 1),
+                           "frac_of_hbm_peak": round(cls["ridge"][2] / max(1e-9, cls["ridge"][0]) / 1e6 / pk["hbm_gbs"], 3),
+                           "share_of_conv_ms": round(cls["ridge"][0] / max(1e-9, total_ms), 3),
+                           "what": "arithmetic intensity within 10 % of the ridge: the fused bottleneck blocks"},
         "hbm_bound_launches": {"launches": cls["hbm"][3], "ms": round(cls["hbm"][0], 3),
                                "gbs": round(cls["hbm"][2] / max(1e-9, cls["hbm"][0]) / 1e6, 1),
                                "frac_of_hbm_peak": round(cls["hbm"][2] / max(1e-9, cls["hbm"][0]) / 1e6 / pk["hbm_gbs"], 3),
@@ -678,7 +688,8 @@ def conv_roofline(net, B, Hp, Wp, dev, dec_slot=0):
     return {"tflops": total_flops / (run_ms / 1e3) / 1e12, "ms": run_ms, "launches": n, "by_class": by_class,
             "by_stage": by_stage, "plan_gflop": total_flops / 1e9,
             "per_launch_events_tflops": total_flops / (total_ms / 1e3) / 1e12,
-            "kernel": "conv_simt_kernel" if net.precision == "fp32" else "conv_halo_kernel (tcgen05 implicit GEMM, halo-resident A tiles)"}
+            "kernel": "conv_simt_kernel" if net.precision == "fp32" else
+                      "conv_halo_kernel (tcgen05 implicit GEMM, halo-resident A tiles) + rb_fused_kernel (fused bottleneck blocks)"}
 
 
 if __name__ == "__main__":
