@@ -461,13 +461,25 @@ conv_halo_kernel(const __grid_constant__ HParams p) {
                 if constexpr (kEpi == RGBD_EPI_SHUFFLE2) {
                     // 16 columns = 4 output parities x 4 channels of a stride-2 transposed conv: pixel shuffle
                     if (valid) {
+                        // bf16 rows padded to >= 4 channels: the 4 columns of a parity leave as ONE 8-byte store (the columns
+                        // beyond Cout have zero weights and zero bias: the padding lanes receive act(0) = 0)
+                        const bool pack4 = sizeof(TOut) == 2 && ((d.y_cstride | d.y_coff) & 3) == 0 &&
+                                           (reinterpret_cast<uintptr_t>(y) & 7) == 0;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int64_t pix = ((int64_t)tc.n * d.Ho + 2 * sy + (q >> 1)) * d.Wo + 2 * sx + (q & 1);
                             TOut *dst = y + pix * d.y_cstride + d.y_coff;
+                            float o[4];
 #pragma unroll
-                            for (int ch = 0; ch < 4; ++ch)
-                                if (ch < d.Cout) ElemIO<TOut>::st(dst + ch, act_fn(v[4 * q + ch] + bias_s[4 * q + ch], slope));
+                            for (int ch = 0; ch < 4; ++ch) o[ch] = act_fn(v[4 * q + ch] + bias_s[4 * q + ch], slope);
+                            if (pack4) {
+                                const __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+                                *reinterpret_cast<uint2 *>(dst) = make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+                            } else {
+#pragma unroll
+                                for (int ch = 0; ch < 4; ++ch)
+                                    if (ch < d.Cout) ElemIO<TOut>::st(dst + ch, o[ch]);
+                            }
                         }
                     }
                     return;
