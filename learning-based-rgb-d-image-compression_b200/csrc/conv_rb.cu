@@ -10,14 +10,15 @@
 // Geometry.  Positions are laid out with a row pitch of P = 32, so one M tile of 128 positions is rpm = 4 whole rows, one
 // epilogue warp (32 TMEM lanes) is one row, and position <-> (row, column) is a shift and a mask.  A tile produces 2 M
 // tiles of output (R = 8 rows x TW = 30 useful columns); its one-pixel halo — 10 rows x 32 columns starting one pixel up
-// and left — fits 3 M tiles (322 of their 384 rows are ever read).  One persistent CTA per SM walks the tiles.  Per tile, three GEMM phases share the tensor pipe:
+// and left — fits 3 M tiles (322 of their 384 rows are ever read).  One persistent CTA per SM takes tiles from a global
+// counter (dynamic scheduler, as in conv_halo.cu).  Per tile, three GEMM phases share the tensor pipe:
 //   P1  t1 = relu(W1 x + b1) on the halo (3 M tiles: 0 and 1 together, one issuer warp each, then 2 — so that the epilogues
-//       of the first two run under the MMAs of the third).  x arrives as 16 KB pieces {64 channels, P columns, rpm rows} = one (channel block, M
-//       tile) each, through a 4-deep TMA ring; the NEXT tile's pieces are prefetched into L2 while this
-//       tile computes (cp.async.bulk.prefetch.tensor), so the ring refills at L2 latency, not HBM latency.  Accumulators
-//       D1[m] in TMEM columns [0, 288).  The epilogue warps turn D1 into bf16 t1 in shared memory (two 128-byte-row planes:
-//       channels 0-63 and 64-95, written with the 128-byte swizzle a TMA load would have produced), forcing positions
-//       outside the image to ZERO — the 3x3 conv of the reference pads t1 with zeros, not with relu(b1).
+//       of the first two run under the MMAs of the third).  x arrives as 16 KB pieces {64 channels, P columns, rpm rows} =
+//       one (channel block, M tile) each, through a 4-deep TMA ring; the NEXT tile's pieces are prefetched into L2 while
+//       this tile computes (cp.async.bulk.prefetch.tensor), so the ring refills at L2 latency, not HBM latency.
+//       Accumulators D1[m] in TMEM columns [0, 288).  The epilogue warps turn D1 into bf16 t1 in shared memory (two
+//       128-byte-row planes: channels 0-63 and 64-95, written with the 128-byte swizzle a TMA load would have produced),
+//       forcing positions outside the image to ZERO — the 3x3 conv of the reference pads t1 with zeros, not with relu(b1).
 //   P2  t2 = relu(W2 (*) t1 + b2): implicit GEMM over the 9 taps; the A operand of tap (ky, kx) is the t1 plane read
 //       through a UMMA descriptor whose start address is shifted by ky * P + kx rows (the halo trick of conv_halo.cu).
 //       D2[j] in TMEM columns [288, 480).  t2 overwrites t1 in shared memory (every P2 MMA has completed by then).
