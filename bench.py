@@ -301,15 +301,11 @@ def run_b200(args):
             def stage_input(j, slot, stream):
                 # pinned HOST tensors straight into the public API: compress_async() copies them into its launch plan's input
                 # buffers on the slot's stream (the H2D copy of this job's images, inside the timed region)
-                if os.environ.get("RGBD_BENCH_DIAG_NO_H2D"):       # diagnostic only (an e2e number without it is not one)
-                    return rgb_d[sl[j % J]], depth_d[sl[j % J]]
                 return rgb_h[sl[j % J]], depth_h[sl[j % J]]
 
             def sink(j, slot, stream, x_r, x_d):
                 # D2H of the reconstruction into pinned host buffers, image by image: a job's 126 MB as ONE copy would hold the
                 # copy engine for milliseconds while other slots' small transfers (decoder states, stream words) queue behind it
-                if os.environ.get("RGBD_BENCH_DIAG_NO_D2H"):       # diagnostic only
-                    return
                 for i in range(x_r.shape[0]):
                     host_out[slot][0][i].copy_(x_r[i], non_blocking=True)
                     host_out[slot][1][i].copy_(x_d[i], non_blocking=True)
@@ -395,13 +391,6 @@ def run_b200(args):
         dist.all_reduce(total_pairs_step, op=dist.ReduceOp.SUM)
     total_pairs_step = int(total_pairs_step.item())
     L.load().rgbd_launch_count(1)
-    e2e_first = os.environ.get("RGBD_BENCH_E2E_FIRST") == "1"      # diagnostic: which leg runs on the cooler GPU
-    if e2e_first:
-        s0 = ClockSampler(local)
-        s0.start()
-        ms_e2e, res2 = timed(steps_e2e, K)
-        clocks_e2e = s0.stop()
-        L.load().rgbd_launch_count(1)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -415,12 +404,11 @@ def run_b200(args):
         add_pair_stats(stats, c["r_strings"], c["d_strings"], rgb_d[s_][:, :, :H, :W], depth_d[s_][:, :, :H, :W],
                        xr[:, :, :H, :W], xd[:, :, :H, :W])
 
-    if not e2e_first:
-        s0 = ClockSampler(local)
-        if rank == 0:
-            s0.start()
-        ms_e2e, res2 = timed(steps_e2e, K)
-        clocks_e2e = s0.stop() if rank == 0 else None
+    s0 = ClockSampler(local)
+    if rank == 0:
+        s0.start()
+    ms_e2e, res2 = timed(steps_e2e, K)
+    clocks_e2e = s0.stop() if rank == 0 else None
     e2e_value = total_pairs_step * K / (ms_e2e / 1e3)
     # bytes per step: every pair's images up, its four strings down and up again (they are host `bytes`), its reconstruction down
     bytes_per_pair_strings = sum(len(x) for _, c, _ in res2 for key in ("r_strings", "d_strings") for grp in c[key]

@@ -600,8 +600,13 @@ extern "C" int rgbd_rb_plan_create(const rgbd_rb_desc *d, rgbd_rb_plan **out) {
     p.nblk3 = d->Cout / kNB3;
     p.final_relu = d->final_relu;
     p.sched = reinterpret_cast<int32_t *>(d->sched_ws);
+    p.prefetch = 1;
+    p.static_tiles = 0;
+#ifdef RGBD_TIMING_PROBES
+    // A / B switches of development builds only (RGBD_BUILD_DEFINES=-DRGBD_TIMING_PROBES)
     p.prefetch = getenv("RGBD_RB_NOPREFETCH") == nullptr;
     p.static_tiles = getenv("RGBD_RB_STATIC") != nullptr;
+#endif
     p.wide_io = ((d->res_cstride | d->res_coff) & 15) == 0 && ((uintptr_t)d->res & 31) == 0;
     p.dbg = nullptr;
 #ifdef RGBD_TIMING_PROBES

@@ -95,12 +95,14 @@ class SymmetricalTransFormerUnited(ELIC_united):
         b.release(h, x1)
         return y
 
-    def _layer(self, b, layer, x, out_dtype=None):
-        """BasicLayer.forward (stf_united.py:328-371): the blocks, then PatchMerging / PatchSplit."""
+    def _layer(self, b, layer, x, out_dtype=None, keep_input=False):
+        """BasicLayer.forward (stf_united.py:328-371): the blocks, then PatchMerging / PatchSplit.  keep_input: x belongs
+        to the caller (the y_hat buffers of the context chain) and is not returned to the plan's arena."""
         n = len(layer.blocks)
         for i, blk in enumerate(layer.blocks):
             y = self._block(b, blk, x, out_dtype=out_dtype if (i == n - 1 and layer.downsample is None) else None)
-            b.release(x)
+            if not (keep_input and i == 0):
+                b.release(x)
             x = y
         ds = layer.downsample
         if isinstance(ds, PatchMerging):
@@ -123,7 +125,7 @@ class SymmetricalTransFormerUnited(ELIC_united):
         b.prog.keep.extend([u.buf, out.buf])
         return out
 
-    def _walk(self, b, rgb_layers, depth_layers, r, d, final_dtype=None):
+    def _walk(self, b, rgb_layers, depth_layers, r, d, final_dtype=None, keep_inputs=False):
         n = len(rgb_layers)
         for i in range(n):
             rm, dm = rgb_layers[i], depth_layers[i]
@@ -136,8 +138,8 @@ class SymmetricalTransFormerUnited(ELIC_united):
                 continue
             assert isinstance(rm, BasicLayer)
             last = i == n - 1
-            r = self._layer(b, rm, r, out_dtype=final_dtype if last else None)
-            d = self._layer(b, dm, d, out_dtype=final_dtype if last else None)
+            r = self._layer(b, rm, r, out_dtype=final_dtype if last else None, keep_input=keep_inputs and i == 0)
+            d = self._layer(b, dm, d, out_dtype=final_dtype if last else None, keep_input=keep_inputs and i == 0)
         return r, d
 
     # ------------------------------------------------------------------ the two hooks of ELIC_united
@@ -162,7 +164,7 @@ class SymmetricalTransFormerUnited(ELIC_united):
 
     def _synthesis(self, b, yhat_r, yhat_d):
         # the y_hat buffers are owned by the chain (and read by the parity tests): the first block must not release them
-        r, d = self._walk(b, self.g_s.rgb_syn_layers, self.g_s.depth_syn_layers, _Keep(yhat_r), _Keep(yhat_d))
+        r, d = self._walk(b, self.g_s.rgb_syn_layers, self.g_s.depth_syn_layers, yhat_r, yhat_d, keep_inputs=True)
         outs = []
         for x, end in ((r, self.g_s.rgb_end_conv), (d, self.g_s.depth_end_conv)):
             t = b.conv(self._pc(end[0]), x)                       # 5x5, embed -> 4 embed
@@ -172,12 +174,6 @@ class SymmetricalTransFormerUnited(ELIC_united):
             outs.append(b.conv(self._pc(end[2]), s))              # 3x3, embed -> 3 / 1
             b.release(s)
         return outs[0], outs[1]
-
-
-def _Keep(view):
-    """A view whose storage release() ignores (it carries no arena range of its own)."""
-    from .engine import View
-    return View(view.buf.view(view.buf.shape), view.coff, view.C)
 
 
 STF_united = SymmetricalTransFormerUnited
