@@ -214,7 +214,7 @@ def run_reference(args):
     # a step = one pair; big images keep the whole run within a few minutes by capping the timed passes
     per_pair_s = 1.5 * (args.height * args.width) / (480 * 640)
     steps = max(1, min(args.steps, int(150 / per_pair_s)))
-    warmup = max(0, min(args.warmup, 1))
+    warmup = max(0, min(args.warmup, max(1, int(20 / per_pair_s))))      # the asked-for warm-up, within ~20 s of CPU time
     cb = cpu_arm(args, 1, steps, warmup)
     line = {"impl": "reference", "metric": metric_name(args), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_pair"], "higher_is_better": True,
