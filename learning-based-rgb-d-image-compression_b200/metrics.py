@@ -83,7 +83,7 @@ def ms_ssim_per_channel(a, b, data_range=1.0, clamp01=True):
                 x, y, clamp = nx, ny, 0          # (the clamp is applied once, when the full-resolution images are read)
     # the last, tiny step on the host in float64: prod_l relu(cs_l)^w_l (l < 4) * relu(ssim_4)^w_4
     s = sums.cpu()
-    val = torch.ones(planes, dtype=torch.float64)
+    val = torch.ones(planes, dtype=torch.float64, device="cpu")     # (explicit: the reference harness makes CUDA the default device)
     for lvl, wgt in enumerate(MS_SSIM_WEIGHTS):
         which = 0 if lvl + 1 == len(MS_SSIM_WEIGHTS) else 1
         mean = (s[lvl, :, which] / counts[lvl]).to(torch.float32).to(torch.float64)      # the package works in fp32
