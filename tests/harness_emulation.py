@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(workdir, cls_name, precision):
+def main(workdir, cls_name, precision, size="150x200"):
     import torch
     import torch.nn.functional as F
     import rgbd_b200
@@ -35,7 +35,8 @@ def main(workdir, cls_name, precision):
     seed_net.update(force=True)
     ckpt_path = os.path.join(workdir, "checkpoint_best_loss.pth.tar")
     torch.save({"state_dict": seed_net.state_dict(), "epoch": 7}, ckpt_path)
-    rgb_cpu, depth_cpu = synthetic_pairs(1, 150, 200, seed=11)      # not a multiple of 64: exercises pad / crop0
+    h0, w0 = (int(v) for v in size.split("x"))
+    rgb_cpu, depth_cpu = synthetic_pairs(1, h0, w0, seed=11)        # not a multiple of 64: exercises pad / crop0
     del seed_net
 
     with warnings.catch_warnings():
@@ -83,7 +84,15 @@ def main(workdir, cls_name, precision):
     # forward() under the same global state
     fwd = net(rgb_pad, depth_pad)
     depth16 = (depth_x_hat * 10000).cpu().squeeze().numpy().astype("uint16")         # tester_united.py:101-108
-    print(json.dumps({
+    extra = {}
+    if min(H, W) > 160:      # utils/metrics.py:8-14 + the exports on the GPU, under the same global state (MS-SSIM needs > 160 px)
+        import numpy as np
+        p_gpu, m_gpu = rgbd_b200.compute_metrics(rgb_x_hat, rgb)
+        d16 = rgbd_b200.metrics.export_depth_u16(depth_x_hat.contiguous(), 10000.0).cpu().numpy()
+        u8 = rgbd_b200.metrics.export_u8(rgb_x_hat.contiguous())
+        extra = {"metrics_psnr_matches": abs(p_gpu - psnr(rgb_x_hat, rgb)) < 1e-3, "ms_ssim": m_gpu,
+                 "depth16_matches": bool(np.array_equal(d16[0], depth16)), "u8_shape": list(u8.shape)}
+    print(json.dumps({**extra,
         "ok": True, "rgb_bpp": rgb_bpp, "depth_bpp": depth_bpp, "shape": list(shape),
         "rgb_psnr": psnr(rgb_x_hat, rgb), "depth_psnr": psnr(depth_x_hat, depth),
         "x_hat_shapes": [list(rgb_x_hat.shape), list(depth_x_hat.shape)],
@@ -95,4 +104,4 @@ def main(workdir, cls_name, precision):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], sys.argv[3])
+    main(*sys.argv[1:5])
